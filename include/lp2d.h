@@ -1,0 +1,146 @@
+/* lp2d.h — C ABI of liblp2d.so, the B200 (sm_100a) backend of the lightprop2d
+ * angular-spectrum propagation hot path.
+ *
+ * The reference (vongostev/lightprop2d, pure Python) has no FFI; its backend seam is
+ * the array module `self.xp` plus `_fft2/_ifft2` and `_np/_asxp` inside `Beam2D`
+ * (lightprop2d/beam2d.py:83, 105-114, 135-187, 207-229).  Each entry point below
+ * replaces the numpy/cupy calls of one Beam2D method; the line numbers cite the
+ * reference code that the call reproduces.  The binding a maintainer would add to
+ * the reference is a ctypes stub, shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every array argument is a DEVICE pointer owned by the
+ *     caller (row-major, C-contiguous, beams stacked along the leading axis) unless
+ *     the name starts with `host_`;
+ *   - complex64 = interleaved float pairs, complex128 = interleaved double pairs;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); every call
+ *     only enqueues work, nothing synchronises;
+ *   - return value 0 = success, otherwise an LP2D_E* code; lp2d_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - the plan is bound to the device that was current when it was created.
+ */
+#ifndef LP2D_H
+#define LP2D_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LP2D_API __attribute__((visibility("default")))
+#else
+#define LP2D_API
+#endif
+
+#define LP2D_VERSION 100
+
+#define LP2D_OK 0
+#define LP2D_EINVAL 1       /* bad argument */
+#define LP2D_EUNSUPPORTED 2 /* grid size / combination not built */
+#define LP2D_ECUDA 3        /* CUDA runtime error (message in lp2d_last_error) */
+
+#define LP2D_C64 0
+#define LP2D_C128 1
+
+/* mask element types accepted by lp2d_mul_fft2 */
+#define LP2D_MASK_COMPLEX 1 /* same complex type as the field */
+#define LP2D_MASK_REAL 2    /* real type of the field (float / double) */
+#define LP2D_MASK_U8 3      /* bytes, non-zero = 1 (numpy bool) */
+
+typedef struct lp2d_plan lp2d_plan;
+
+LP2D_API int lp2d_version(void);
+LP2D_API const char* lp2d_last_error(void);
+
+/* Smallest / largest supported npoints (powers of two in between are supported). */
+LP2D_API int lp2d_min_npoints(void);
+LP2D_API int lp2d_max_npoints(int dtype);
+
+/* Host helper: the grids of Beam2D._construct_grids (beam2d.py:299-308) with the
+ * same IEEE operation order: dL = area/n; X[k] = (k - ceil(n/2)) * dL for the
+ * arange(-n//2, n//2) of the reference; Kx = fftfreq(n, dL) = idx * (1/(n*dL));
+ * a[i] = k0*k0 - Kx[i]^2, b[j] = Kx[j]^2 (so Kz[j][i] = sqrt(a[i] - b[j]), NaN -> 0);
+ * x2[i] = X[i]^2.  Any output pointer may be NULL.  All arrays are HOST, length n. */
+LP2D_API int lp2d_grid_tables(int n, double area_size, double wl, double* host_X, double* host_Kx,
+                     double* host_a, double* host_b, double* host_x2);
+
+/* Plan: twiddle tables and the three FP64 tables (copied from host) for an n x n
+ * grid of the given complex type.  Replaces the per-object grid state of
+ * Beam2D.__post_init__ / _construct_grids (beam2d.py:93-133, 290-308). */
+LP2D_API int lp2d_plan_create(lp2d_plan** plan, int n, int dtype, const double* host_a,
+                     const double* host_b, const double* host_x2);
+LP2D_API int lp2d_plan_destroy(lp2d_plan* plan);
+
+/* _fft2 / _ifft2 (beam2d.py:207-229): 2-D DFT over the last two axes of `batch`
+ * planes; forward unscaled, inverse scaled by 1/n^2.  `out` may equal `in`. */
+LP2D_API int lp2d_fft2(lp2d_plan* plan, const void* in, void* out, long long batch, int inverse,
+              void* stream);
+
+/* Beam2D.propagate, stateful form (beam2d.py:481-490): spectrum *= H(z) in place,
+ * field = ifft2(spectrum).  `intensity` (real, may be NULL) receives |field|^2
+ * (iprofile, beam2d.py:717) from the same pass.  z == 0 is the caller's early
+ * return. */
+LP2D_API int lp2d_propagate(lp2d_plan* plan, void* spectrum, void* field, void* intensity,
+                   long long batch, double z, void* stream);
+
+/* Fresh chain for ensembles: field_out = ifft2(fft2(field_in) * H(z)) in three
+ * passes without materialising the spectrum (unless spectrum_out != NULL, which
+ * receives fft2(field_in) * H(z), the spectrum state the reference would hold).
+ * field_out may be NULL when only `intensity` is wanted; then `work` (>= one plane
+ * of complex samples, work_bytes long) carries the intermediates.  field_out may
+ * equal field_in. */
+LP2D_API int lp2d_propagate_field(lp2d_plan* plan, const void* field_in, void* field_out,
+                         void* spectrum_out, void* intensity, void* work,
+                         long long work_bytes, long long batch, double z, void* stream);
+
+/* Beam2D.lens (beam2d.py:508-511): field *= exp(i (X^2+Y^2) k0 / (2f)) in place
+ * (k0 = 1/wl, as the reference), spectrum = fft2(field). */
+LP2D_API int lp2d_lens(lp2d_plan* plan, void* field, void* spectrum, long long batch, double k0,
+              double f, void* stream);
+
+/* coordinate_filter / spectral_filter with an array mask (beam2d.py:338-342,
+ * 369-373): data *= mask in place (mask NULL = no multiply), then
+ * other = fft2(data) (inverse = 0) or ifft2(data) (inverse = 1).
+ * mask_beam_stride = 0 broadcasts one n x n mask over the batch. */
+LP2D_API int lp2d_mul_fft2(lp2d_plan* plan, void* data, void* other, const void* mask, int mask_kind,
+                  long long mask_beam_stride, long long batch, int inverse, void* stream);
+
+/* iprofile (beam2d.py:717): out = |field|^2 (float for complex64, double for complex128). */
+LP2D_API int lp2d_intensity(lp2d_plan* plan, const void* field, void* out, long long batch, void* stream);
+
+/* Beam2D.expand (beam2d.py:392-401): edge-replicating pad of every n_in x n_in plane to
+ * n_out x n_out ((n_out - n_in) even, the same pad on every side).  No plan needed. */
+LP2D_API int lp2d_expand(int dtype, const void* in, void* out, int n_in, int n_out, long long batch,
+                void* stream);
+
+/* Beam2D.coarse (beam2d.py:456-459): mean over m x m blocks, n_in x n_in -> n_in/m x n_in/m. */
+LP2D_API int lp2d_coarse(int dtype, const void* in, void* out, int n_in, int m, long long batch,
+                void* stream);
+
+/* phiprofile (beam2d.py:734): out = atan2(im, re) for `count` samples. */
+LP2D_API int lp2d_phase(int dtype, const void* field, void* out, long long count, void* stream);
+
+/* centroid / D4sigma sums (beam2d.py:680-684, 696-702) of ONE n x n field, FP64:
+ * out5 (device) = [sum I, sum x I, sum y I, sum (x-xc)^2 I, sum (y-yc)^2 I],
+ * x = (col - n/2) dL, y = (row - n/2) dL, I = |field|^2 in the field's real type. */
+LP2D_API int lp2d_moments(int dtype, const void* field, int n, double dL, double xc, double yc,
+                 double* out5, void* stream);
+
+/* deconstruct_by_modes(mode='scalar') (beam2d.py:592-600): coeffs[b][k] =
+ * sum_p modes[k][p] * field_b[centre nb x nb crop][p]  (no conjugation).
+ * modes: nmodes x nb*nb, coeffs: batch x nmodes, same complex type as the field. */
+LP2D_API int lp2d_modes_project(int dtype, const void* field, const void* modes, void* coeffs, int n,
+                       int nb, int nmodes, long long batch, void* stream);
+
+/* construct_by_modes (beam2d.py:552-562, 664-666): field_b = sum_k coeffs[b][k] * mode_k
+ * zero-padded from nb x nb to the centred window of the n x n grid. */
+LP2D_API int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void* field, int n,
+                          int nb, int nmodes, long long batch, void* stream);
+
+/* How many kernels this library has launched in this process (for bench accounting). */
+LP2D_API long long lp2d_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LP2D_H */

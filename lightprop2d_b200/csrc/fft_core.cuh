@@ -1,0 +1,209 @@
+// In-register radix butterflies and the per-line Stockham pass schedule.
+//
+// A "line" is one 1-D transform of length N (a grid row or a grid column).  It is
+// processed by TPL = N / E threads; every thread keeps E complex samples in
+// registers at line positions  t + TPL*m  (m = 0..E-1).  That ownership pattern is
+// (a) what a coalesced global load/store wants (consecutive threads touch
+// consecutive samples) and (b) invariant under the autosort passes below, so the
+// first load and the last store go straight between HBM and registers and only
+// the passes in between exchange data through shared memory.
+//
+// Pass p uses radix R_p (R_p <= E, so each thread runs E/R_p butterflies) with
+// Ns_p = prod_{q<p} R_q:
+//     j      = t + TPL*q                      butterfly index, q < E/R_p
+//     in[r]  = x[j + r*N/R_p]                 == register slot q + r*(E/R_p)
+//     in[r] *= exp(-2*pi*i * (j mod Ns) * r / (Ns*R_p))          (table lookup)
+//     out    = DFT_R(in)
+//     y[(j/Ns)*Ns*R + (j mod Ns) + r*Ns] = out[r]
+// After the last pass (Ns*R == N) the destination index is again j + r*N/R, i.e.
+// the thread's own register slots: natural-order output, no bit reversal pass.
+//
+// The inverse transform is the same code with re/im swapped on the way in and on
+// the way out (ifft(x) = swap(fft(swap(x))) / N).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace lp2d {
+
+template <typename T> struct Cx2;
+template <> struct Cx2<float>  { using type = float2; };
+template <> struct Cx2<double> { using type = double2; };
+template <typename T> using cx = typename Cx2<T>::type;
+
+template <typename T> __host__ __device__ __forceinline__ cx<T> mk(T a, T b) { cx<T> r; r.x = a; r.y = b; return r; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+template <typename C> __device__ __forceinline__ C cswap(C a) { C r; r.x = a.y; r.y = a.x; return r; }
+
+// cos(2*pi*k/32), k = 0..8
+__host__ __device__ constexpr double kCos32(int k) {
+    return k == 0 ? 1.0
+         : k == 1 ? 0.98078528040323044912618223613424
+         : k == 2 ? 0.92387953251128675612818318939679
+         : k == 3 ? 0.83146961230254523707878837761791
+         : k == 4 ? 0.70710678118654752440084436210485
+         : k == 5 ? 0.55557023301960222474283081394853
+         : k == 6 ? 0.38268343236508977172845998403040
+         : k == 7 ? 0.19509032201612826784828486847702
+         : 0.0;
+}
+
+// d * exp(-2*pi*i * k32 / 32) for 0 <= k32 < 16 (k32 is a compile-time value after unrolling)
+template <typename T>
+__device__ __forceinline__ cx<T> mul_w32(cx<T> d, int k32) {
+    if (k32 == 0) return d;
+    if (k32 == 8) return mk<T>(d.y, -d.x);                       // * (-i)
+    if (k32 == 4) {                                              // * (1-i)/sqrt2
+        const T h = (T)kCos32(4);
+        return mk<T>((d.x + d.y) * h, (d.y - d.x) * h);
+    }
+    if (k32 == 12) {                                             // * (-1-i)/sqrt2
+        const T h = (T)kCos32(4);
+        return mk<T>((d.y - d.x) * h, -(d.x + d.y) * h);
+    }
+    // general: w = c - i s  with c = cos(2 pi k/32), s = sin(2 pi k/32)
+    const T c = (T)(k32 <= 8 ? kCos32(k32) : -kCos32(16 - k32));
+    const T s = (T)(k32 <= 8 ? kCos32(8 - k32) : kCos32(k32 - 8));
+    return mk<T>(d.x * c + d.y * s, d.y * c - d.x * s);
+}
+
+__host__ __device__ constexpr int ilog2(int v) { int l = 0; while (v > 1) { v >>= 1; ++l; } return l; }
+__host__ __device__ constexpr int bitrev(int k, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((k >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+// R-point forward DFT on registers, natural order in and out (R = 2..32, power of two).
+// Radix-2 decimation in frequency; the twiddles and the final bit reversal are
+// compile-time after unrolling (register renaming only).
+template <typename T, int R>
+__device__ __forceinline__ void dft_reg(cx<T> (&x)[R]) {
+    static_assert(R >= 1 && R <= 32 && (R & (R - 1)) == 0, "radix");
+    if (R == 1) return;
+#pragma unroll
+    for (int s = R / 2; s >= 1; s >>= 1) {
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            const int pos = k % s;
+            const int i0 = (k / s) * 2 * s + pos;
+            const int i1 = i0 + s;
+            const cx<T> a = x[i0], b = x[i1];
+            x[i0] = cadd(a, b);
+            x[i1] = mul_w32<T>(csub(a, b), pos * (16 / s));
+        }
+    }
+    cx<T> y[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) y[k] = x[bitrev(k, ilog2(R))];
+#pragma unroll
+    for (int k = 0; k < R; ++k) x[k] = y[k];
+}
+
+// ------------------------------------------------------------------ pass schedule
+template <int N, int E>
+struct LinePlan {
+    static_assert((N & (N - 1)) == 0 && (E & (E - 1)) == 0 && E <= N && E <= 32 && E >= 2, "sizes");
+    static constexpr int TPL = N / E;                       // threads per line
+    __host__ __device__ static constexpr int npass() {
+        int n = 0, rem = N;
+        while (rem > 1) { rem /= (E < rem ? E : rem); ++n; }
+        return n;
+    }
+    __host__ __device__ static constexpr int radix(int p) {
+        int rem = N, r = 1;
+        for (int i = 0; i <= p; ++i) { r = (E < rem ? E : rem); rem /= r; }
+        return r;
+    }
+    __host__ __device__ static constexpr int ns(int p) {    // product of the radices before pass p
+        int v = 1;
+        for (int i = 0; i < p; ++i) v *= radix(i);
+        return v;
+    }
+    // twiddle table: for pass p >= 1, entry (r-1)*Ns + k = exp(-2 pi i k r / (Ns R)), r = 1..R-1, k < Ns
+    __host__ __device__ static constexpr int tw_offset(int p) {
+        int off = 0;
+        for (int i = 1; i < p; ++i) off += (radix(i) - 1) * ns(i);
+        return off;
+    }
+    __host__ __device__ static constexpr int tw_size() { return tw_offset(npass()); }
+    // shared-memory padding: one extra slot every PADSTEP samples so that the
+    // stride-R scatter of pass 0 (Ns = 1) spreads over the banks
+    static constexpr int PADSTEP = (radix(0) < 16 ? 16 : radix(0));
+    __host__ __device__ static constexpr int pad(int i) { return i + i / PADSTEP; }
+    static constexpr int LINE_SLOTS = N + N / PADSTEP;      // padded samples per line
+};
+
+// How the TPL threads of one line synchronise around a shared-memory exchange.
+enum { SYNC_WARP = 0, SYNC_NAMED = 1, SYNC_CTA = 2 };
+
+template <int MODE, int TPL>
+__device__ __forceinline__ void line_sync(int line_in_cta) {
+    if (MODE == SYNC_WARP) {
+        __syncwarp();
+    } else if (MODE == SYNC_NAMED) {
+        asm volatile("bar.sync %0, %1;" ::"r"(line_in_cta + 1), "r"(TPL) : "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
+// One pass of the schedule on the thread's registers v[E].
+template <typename T, int N, int E, int P, int SYNC>
+__device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sline,
+                                          const cx<T>* __restrict__ tw, int t, int line_in_cta) {
+    using LP = LinePlan<N, E>;
+    constexpr int R = LP::radix(P);
+    constexpr int Ns = LP::ns(P);
+    constexpr int Q = E / R;
+    constexpr int TPL = LP::TPL;
+    constexpr bool last = (Ns * R == N);
+    constexpr int twoff = LP::tw_offset(P);
+
+    if (P > 0) {
+        // registers of the previous pass were scattered to smem; previous readers are done
+        line_sync<SYNC, TPL>(line_in_cta);
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = sline[LP::pad(t + TPL * m)];
+    }
+    if (!last) {
+        // everyone has read its inputs before anyone overwrites the exchange buffer
+        line_sync<SYNC, TPL>(line_in_cta);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int j = t + TPL * q;
+        cx<T> u[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
+        if (Ns > 1) {
+            const int k = j & (Ns - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+        }
+        dft_reg<T, R>(u);
+        if (last) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q + r * Q] = u[r];
+        } else {
+            const int base = (j / Ns) * (Ns * R) + (j & (Ns - 1));
+#pragma unroll
+            for (int r = 0; r < R; ++r) sline[LP::pad(base + r * Ns)] = u[r];
+        }
+    }
+}
+
+// Forward FFT of the line held in v (natural-strided ownership in, same out).
+// Exchange-buffer contract: every scatter is preceded by a sync of the line's
+// threads, so back-to-back calls on the same sline (next line of a loop, or the
+// inverse transform that follows the transfer function) need no extra barrier.
+template <typename T, int N, int E, int SYNC, int P = 0>
+__device__ __forceinline__ void line_fft(cx<T> (&v)[E], cx<T>* sline, const cx<T>* tw, int t, int line_in_cta) {
+    line_pass<T, N, E, P, SYNC>(v, sline, tw, t, line_in_cta);
+    if constexpr (P + 1 < LinePlan<N, E>::npass()) line_fft<T, N, E, SYNC, P + 1>(v, sline, tw, t, line_in_cta);
+}
+
+}  // namespace lp2d

@@ -1,0 +1,250 @@
+// The line kernel: one CTA transforms W lines (rows or a tile of W adjacent
+// columns) of one beam, with the pointwise stages of the propagation path fused
+// around the transform:
+//
+//   load -> [mask multiply] -> [lens phase | transfer function H]  -> [store state]
+//        -> FFT (forward or inverse)  or  FFT -> H -> inverse FFT (fused column pass)
+//        -> scale -> [store field/spectrum] [store |E|^2]
+//
+// Rows are contiguous: consecutive threads load consecutive samples.  Columns are
+// processed W at a time so that every global access of a warp is made of W*sizeof
+// contiguous bytes per grid row (64 B for W=8 complex64).
+//
+// Reference semantics reproduced here (lightprop2d/beam2d.py, /root/reference):
+//   * H = exp(i*2*pi*(trunc(Kz*z) - Kz*z)), Kz = nan_to_num(sqrt(k0^2 - Kx^2 - Ky^2)),
+//     phase formed in FP64 with the reference's operation order (beam2d.py:307-308,
+//     485-489); Kz^2 comes from two host-built FP64 tables a[i] = k0^2 - Kx[i]^2 and
+//     b[j] = Ky[j]^2 so the subtraction order matches numpy's broadcasting bit for bit.
+//   * lens phase (X^2 + Y^2) * k0 / (2 f) in FP64, k0 = 1/wl (beam2d.py:508-510).
+//   * inverse transform scaled by 1/N per axis (numpy ifft2 convention).
+#pragma once
+#include "fft_core.cuh"
+
+namespace lp2d {
+
+enum { AX_ROW = 0, AX_COL = 1 };
+enum { PRE_NONE = 0, PRE_LENS = 1, PRE_H = 2 };
+enum { MID_NONE = 0, MID_H = 1 };
+enum { F_INVERSE = 1 };
+enum { MASK_NONE = 0, MASK_CX = 1, MASK_REAL = 2, MASK_U8 = 3 };
+
+template <typename T>
+struct LineArgs {
+    const cx<T>* in;        // input plane(s)
+    cx<T>* out;             // transformed output (may alias in), or nullptr
+    cx<T>* out_pre;         // state after the pointwise pre-stage (spectrum*H, field*lens, field*mask), or nullptr
+    cx<T>* out_mid;         // fused column pass only: the 2-D spectrum after H (reference's spectrum state), or nullptr
+    T* inten;               // |out|^2, or nullptr
+    const void* mask;       // optional multiplier applied at load
+    const cx<T>* tw;        // twiddle table of the (N, E) plan
+    const double* a_tab;    // k0^2 - Kx[i]^2
+    const double* b_tab;    // Ky[j]^2
+    const double* x2_tab;   // X[i]^2
+    double z;               // propagation distance
+    double lens_k0;         // 1 / wl
+    double lens_2f;         // 2 * f
+    T scale;                // applied to the output of the transform
+    long long beam_stride;  // samples between consecutive beams (N*N)
+    long long mask_beam_stride;  // 0: one mask for every beam
+    int nlines;             // rows: beams*N; columns: beams*N/W tiles
+    int mask_kind;
+    int flags;
+};
+
+// ---------------------------------------------------------------- pointwise factors
+template <typename T> struct Trig;
+template <> struct Trig<float> {
+    // cycles in (-1, 1) -> (cos, sin) of 2*pi*cycles
+    __device__ __forceinline__ static float2 unit_from_cycles(double cyc) {
+        float s, c;
+        sincospif(2.0f * (float)cyc, &s, &c);
+        return make_float2(c, s);
+    }
+    __device__ __forceinline__ static float2 unit_from_radians(double ph) {
+        // range-reduce in FP64, evaluate in FP32
+        double r = ph * 0.15915494309189533576888376337251;   // 1/(2 pi)
+        r -= rint(r);
+        return unit_from_cycles(r);
+    }
+};
+template <> struct Trig<double> {
+    __device__ __forceinline__ static double2 unit_from_cycles(double cyc) {
+        double s, c;
+        sincospi(2.0 * cyc, &s, &c);
+        return make_double2(c, s);
+    }
+    __device__ __forceinline__ static double2 unit_from_radians(double ph) {
+        double s, c;
+        sincos(ph, &s, &c);
+        return make_double2(c, s);
+    }
+};
+
+// exp(i*2*pi*(trunc(Kz z) - Kz z)); a_i - b_j is Kz^2 exactly as the reference forms it
+template <typename T>
+__device__ __forceinline__ cx<T> transfer_factor(double a_i, double b_j, double z) {
+    const double s = __dsub_rn(a_i, b_j);
+    const double kz = (s > 0.0) ? __dsqrt_rn(s) : 0.0;      // NaN (evanescent) -> 0 -> H = 1
+    const double d = __dmul_rn(kz, z);
+    const double fr = __dsub_rn(trunc(d), d);                // exact; in (-1, 1)
+    return Trig<T>::unit_from_cycles(fr);
+}
+
+template <typename T>
+__device__ __forceinline__ cx<T> lens_factor(double x2_i, double y2_j, double k0, double two_f) {
+    const double ph = __ddiv_rn(__dmul_rn(__dadd_rn(x2_i, y2_j), k0), two_f);
+    return Trig<T>::unit_from_radians(ph);
+}
+
+// ------------------------------------------------------------------ configuration
+template <typename T, int N, int E, int AXIS, int W>
+struct KCfg {
+    using LP = LinePlan<N, E>;
+    static constexpr int TPL = LP::TPL;
+    static constexpr int THREADS = W * TPL;
+    static constexpr int SYNC = (AXIS == AX_COL) ? (THREADS <= 32 ? SYNC_WARP : SYNC_CTA)
+                              : (TPL <= 32 ? SYNC_WARP : (W == 1 ? SYNC_CTA : SYNC_NAMED));
+    static constexpr int S128 = 128 / (int)sizeof(cx<T>);          // samples per 128 B
+    static constexpr int RES = (AXIS == AX_COL) ? (W >= S128 ? 1 : S128 / W) : (TPL < S128 ? TPL : 0);
+    static constexpr int LS = LP::LINE_SLOTS + ((RES - LP::LINE_SLOTS % S128) + S128) % S128;
+    static constexpr size_t SMEM = (LP::npass() > 1) ? (size_t)W * LS * sizeof(cx<T>) : 0;
+    static_assert(THREADS <= 1024, "block too large");
+    static_assert(SYNC != SYNC_NAMED || (W <= 15 && TPL % 32 == 0), "named barriers");
+};
+
+template <typename T, int N, int E, int AXIS, int W, int PRE, int MID>
+__global__ void __launch_bounds__(KCfg<T, N, E, AXIS, W>::THREADS)
+line_kernel(const LineArgs<T> p) {
+    using K = KCfg<T, N, E, AXIS, W>;
+    constexpr int TPL = K::TPL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int l = (AXIS == AX_ROW) ? tid / TPL : tid % W;     // line within the CTA
+    const int t = (AXIS == AX_ROW) ? tid % TPL : tid / W;     // thread within the line
+    cx<T>* sline = smem + l * K::LS;
+
+    // which line of which beam; "fixed" is the grid index that is constant along the line
+    long long base;
+    int fixed;
+    bool active;
+    long long mbase = 0;
+    if constexpr (AXIS == AX_ROW) {
+        const long long line = (long long)blockIdx.x * W + l;
+        active = line < p.nlines;
+        const long long beam = line / N;
+        fixed = (int)(line % N);                              // row j
+        base = beam * p.beam_stride + (long long)fixed * N;
+        mbase = beam * p.mask_beam_stride + (long long)fixed * N;
+    } else {
+        constexpr int TILES = N / W;
+        const long long tile = blockIdx.x;
+        active = tile < p.nlines;
+        const long long beam = tile / TILES;
+        fixed = (int)(tile % TILES) * W + l;                  // column i
+        base = beam * p.beam_stride + fixed;
+        mbase = beam * p.mask_beam_stride + fixed;
+    }
+    constexpr long long STRIDE = (AXIS == AX_ROW) ? 1 : N;
+
+    cx<T> v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int pos = t + TPL * m;
+        v[m] = active ? p.in[base + pos * STRIDE] : mk<T>(0, 0);
+    }
+
+    if (p.mask_kind != MASK_NONE && active) {
+        if (p.mask_kind == MASK_CX) {
+            const cx<T>* mk_ = static_cast<const cx<T>*>(p.mask);
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], mk_[mbase + (t + TPL * m) * STRIDE]);
+        } else if (p.mask_kind == MASK_REAL) {
+            const T* mk_ = static_cast<const T*>(p.mask);
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const T f = mk_[mbase + (t + TPL * m) * STRIDE];
+                v[m].x *= f; v[m].y *= f;
+            }
+        } else {
+            const unsigned char* mk_ = static_cast<const unsigned char*>(p.mask);
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const T f = mk_[mbase + (t + TPL * m) * STRIDE] ? (T)1 : (T)0;
+                v[m].x *= f; v[m].y *= f;
+            }
+        }
+    }
+
+    if (PRE == PRE_LENS) {
+        const double f2 = __ldg(&p.x2_tab[fixed]);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const double g2 = __ldg(&p.x2_tab[t + TPL * m]);
+            // (X^2 + Y^2): X indexes columns, Y rows; the sum is commutative so the order is immaterial
+            v[m] = cmul(v[m], lens_factor<T>(AXIS == AX_ROW ? g2 : f2, AXIS == AX_ROW ? f2 : g2, p.lens_k0, p.lens_2f));
+        }
+    }
+    if (PRE == PRE_H) {
+        // rows: fixed = j -> b[j]; columns: fixed = i -> a[i]
+        const double fx = (AXIS == AX_ROW) ? __ldg(&p.b_tab[fixed]) : __ldg(&p.a_tab[fixed]);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int pos = t + TPL * m;
+            const double a_i = (AXIS == AX_ROW) ? __ldg(&p.a_tab[pos]) : fx;
+            const double b_j = (AXIS == AX_ROW) ? fx : __ldg(&p.b_tab[pos]);
+            v[m] = cmul(v[m], transfer_factor<T>(a_i, b_j, p.z));
+        }
+    }
+    if (p.out_pre != nullptr && active) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) p.out_pre[base + (t + TPL * m) * STRIDE] = v[m];
+    }
+
+    if (MID == MID_H) {
+        // column pass of the fresh chain: FFT_y, transfer function, inverse FFT_y
+        line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
+        const double a_i = __ldg(&p.a_tab[fixed]);            // AXIS == AX_COL
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const cx<T> h = transfer_factor<T>(a_i, __ldg(&p.b_tab[t + TPL * m]), p.z);
+            v[m] = cmul(v[m], h);
+        }
+        if (p.out_mid != nullptr && active) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) p.out_mid[base + (t + TPL * m) * STRIDE] = v[m];
+        }
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+        line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    } else {
+        const bool inv = (p.flags & F_INVERSE) != 0;
+        if (inv) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+        }
+        line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
+        if (inv) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+        }
+    }
+
+    if (!active) return;
+    const T sc = p.scale;
+#pragma unroll
+    for (int m = 0; m < E; ++m) { v[m].x *= sc; v[m].y *= sc; }
+    if (p.out != nullptr) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) p.out[base + (t + TPL * m) * STRIDE] = v[m];
+    }
+    if (p.inten != nullptr) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) p.inten[base + (t + TPL * m) * STRIDE] = v[m].x * v[m].x + v[m].y * v[m].y;
+    }
+}
+
+}  // namespace lp2d

@@ -1,0 +1,380 @@
+// C ABI of liblp2d.so (see include/lp2d.h).  Host-side orchestration only: which
+// line kernels run, in which order, over which chunk of the batch.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lp2d.h"
+#include "dispatch.h"
+
+namespace lp2d {
+long long g_launches = 0;
+
+static thread_local std::string t_err;
+
+static int fail(int code, const std::string& msg) {
+    t_err = msg;
+    return code;
+}
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(LP2D_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// |field|^2, vectorised two samples per thread-iteration
+template <typename T>
+__global__ void intensity_kernel(const cx<T>* __restrict__ f, T* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const cx<T> v = f[i];
+        out[i] = v.x * v.x + v.y * v.y;
+    }
+}
+}  // namespace lp2d
+
+using namespace lp2d;
+
+struct lp2d_plan {
+    int device;
+    int n;
+    int dtype;
+    const SizeOps<float>* ops32;
+    const SizeOps<double>* ops64;
+    void* tw;          // device twiddles (cx<T>)
+    double* tabs;      // device: a | b | x2, n doubles each
+    long long chunk_bytes;   // intermediate kept per kernel pair (L2 residency)
+};
+
+#define LP2D_CHECK_PLAN(p)                                                      \
+    do {                                                                        \
+        if ((p) == nullptr) return fail(LP2D_EINVAL, "plan is NULL");           \
+    } while (0)
+
+extern "C" {
+
+int lp2d_version(void) { return LP2D_VERSION; }
+const char* lp2d_last_error(void) { return t_err.c_str(); }
+long long lp2d_launch_count(void) { return g_launches; }
+int lp2d_min_npoints(void) { return 16; }
+int lp2d_max_npoints(int dtype) { return dtype == LP2D_C64 ? 8192 : 4096; }
+
+int lp2d_grid_tables(int n, double area_size, double wl, double* X, double* Kx, double* a,
+                     double* b, double* x2) {
+    if (n <= 0 || !(area_size > 0) || !(wl > 0)) return fail(LP2D_EINVAL, "grid_tables: bad n/area_size/wl");
+    const double dL = area_size / (double)n;              // beam2d.py:299
+    const double k0 = 1.0 / wl;                           // :304
+    const double k0sq = k0 * k0;
+    const double val = 1.0 / ((double)n * dL);            // numpy fftfreq: 1.0/(n*d)
+    const int first = -((n + 1) / 2);                     // Python: -n // 2
+    const int npos = (n - 1) / 2 + 1;                     // fftfreq: 0..(n-1)//2 then -(n//2)..-1
+    for (int k = 0; k < n; ++k) {
+        const double x = (double)(first + k) * dL;        // :300-301
+        const int idx = k < npos ? k : k - n;
+        const double kx = (double)idx * val;              // :305
+        if (X) X[k] = x;
+        if (x2) x2[k] = x * x;
+        if (Kx) Kx[k] = kx;
+        if (a) a[k] = k0sq - kx * kx;                     // :307-308, left-to-right
+        if (b) b[k] = kx * kx;
+    }
+    return LP2D_OK;
+}
+
+int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, const double* host_b,
+                     const double* host_x2) {
+    if (out == nullptr) return fail(LP2D_EINVAL, "plan_create: out is NULL");
+    *out = nullptr;
+    if (dtype != LP2D_C64 && dtype != LP2D_C128) return fail(LP2D_EINVAL, "plan_create: dtype must be LP2D_C64 or LP2D_C128");
+    if (host_a == nullptr || host_b == nullptr || host_x2 == nullptr)
+        return fail(LP2D_EINVAL, "plan_create: grid tables must not be NULL");
+    const SizeOps<float>* o32 = dtype == LP2D_C64 ? find_ops_f32(n) : nullptr;
+    const SizeOps<double>* o64 = dtype == LP2D_C128 ? find_ops_f64(n) : nullptr;
+    if (o32 == nullptr && o64 == nullptr) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "plan_create: npoints=%d not supported for %s (powers of two %d..%d)", n,
+                 dtype == LP2D_C64 ? "complex64" : "complex128", lp2d_min_npoints(), lp2d_max_npoints(dtype));
+        return fail(LP2D_EUNSUPPORTED, buf);
+    }
+    cudaError_t e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if ((e = (o32 ? o32->configure() : o64->configure())) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+
+    lp2d_plan* p = new lp2d_plan();
+    p->device = dev; p->n = n; p->dtype = dtype; p->ops32 = o32; p->ops64 = o64;
+    p->tw = nullptr; p->tabs = nullptr;
+    const char* env = getenv("LP2D_CHUNK_MB");
+    p->chunk_bytes = (env ? atoll(env) : 32) * (1ll << 20);
+    if (p->chunk_bytes <= 0) p->chunk_bytes = 1ll << 62;
+
+    std::vector<double> w;
+    if (o32) o32->twiddles(w); else o64->twiddles(w);
+    const size_t ntw = w.size() / 2;
+    const size_t tw_bytes = (ntw ? ntw : 1) * (dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2));
+    if ((e = cudaMalloc(&p->tw, tw_bytes)) != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(twiddles)"); }
+    if (ntw) {
+        if (dtype == LP2D_C64) {
+            std::vector<float> wf(w.size());
+            for (size_t i = 0; i < w.size(); ++i) wf[i] = (float)w[i];
+            e = cudaMemcpy(p->tw, wf.data(), tw_bytes, cudaMemcpyHostToDevice);
+        } else {
+            e = cudaMemcpy(p->tw, w.data(), tw_bytes, cudaMemcpyHostToDevice);
+        }
+        if (e != cudaSuccess) { cudaFree(p->tw); delete p; return cuda_fail(e, "cudaMemcpy(twiddles)"); }
+    }
+    if ((e = cudaMalloc(&p->tabs, 3 * sizeof(double) * n)) != cudaSuccess) { cudaFree(p->tw); delete p; return cuda_fail(e, "cudaMalloc(tables)"); }
+    if ((e = cudaMemcpy(p->tabs, host_a, sizeof(double) * n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(p->tabs + n, host_b, sizeof(double) * n, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(p->tabs + 2 * n, host_x2, sizeof(double) * n, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(p->tw); cudaFree(p->tabs); delete p;
+        return cuda_fail(e, "cudaMemcpy(tables)");
+    }
+    *out = p;
+    return LP2D_OK;
+}
+
+int lp2d_plan_destroy(lp2d_plan* p) {
+    if (p == nullptr) return LP2D_OK;
+    cudaFree(p->tw);
+    cudaFree(p->tabs);
+    delete p;
+    return LP2D_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ typed drivers
+namespace {
+
+template <typename T> const SizeOps<T>* ops_of(const lp2d_plan* p);
+template <> const SizeOps<float>* ops_of<float>(const lp2d_plan* p) { return p->ops32; }
+template <> const SizeOps<double>* ops_of<double>(const lp2d_plan* p) { return p->ops64; }
+
+template <typename T>
+LineArgs<T> base_args(const lp2d_plan* p) {
+    LineArgs<T> a;
+    memset(&a, 0, sizeof a);
+    a.tw = static_cast<const cx<T>*>(p->tw);
+    a.a_tab = p->tabs;
+    a.b_tab = p->tabs + p->n;
+    a.x2_tab = p->tabs + 2 * p->n;
+    a.scale = (T)1;
+    a.beam_stride = (long long)p->n * p->n;
+    return a;
+}
+
+// beams per kernel pair so that the intermediate plane(s) stay L2 resident
+template <typename T>
+long long chunk_beams(const lp2d_plan* p, long long batch) {
+    const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
+    long long c = p->chunk_bytes / plane;
+    if (c < 1) c = 1;
+    // keep the row-count of a launch inside int range
+    const long long cap = (long long)(0x7fffffff) / p->n;
+    if (c > cap) c = cap;
+    return c < batch ? c : batch;
+}
+
+#define LP2D_CU(call, what)                                         \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail(e__, what);        \
+    } while (0)
+
+template <typename T>
+int rows(const lp2d_plan* p, int pre, LineArgs<T> a, long long beams, cudaStream_t s) {
+    a.nlines = (int)(beams * p->n);
+    LP2D_CU(ops_of<T>(p)->row(pre, a, s), "row pass launch");
+    return LP2D_OK;
+}
+template <typename T>
+int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream_t s) {
+    a.nlines = (int)(beams * (p->n / ops_of<T>(p)->w_col));
+    LP2D_CU(ops_of<T>(p)->col(mid, a, s), "column pass launch");
+    return LP2D_OK;
+}
+
+// data *= mask (optional), state stored to `data`, other = (i)fft2(data)
+template <typename T>
+int mul_fft2(const lp2d_plan* p, const void* in, void* state_out, void* other, const void* mask, int mask_kind,
+             long long mask_stride, long long batch, int inverse, int pre, double k0, double two_f, cudaStream_t s) {
+    const long long plane = (long long)p->n * p->n;
+    const long long cb = chunk_beams<T>(p, batch);
+    const T sc = inverse ? (T)(1.0 / (double)p->n) : (T)1;
+    for (long long b0 = 0; b0 < batch; b0 += cb) {
+        const long long nb = (batch - b0 < cb) ? batch - b0 : cb;
+        LineArgs<T> a = base_args<T>(p);
+        a.in = static_cast<const cx<T>*>(in) + b0 * plane;
+        a.out = static_cast<cx<T>*>(other) + b0 * plane;
+        a.out_pre = state_out ? static_cast<cx<T>*>(state_out) + b0 * plane : nullptr;
+        a.flags = inverse ? F_INVERSE : 0;
+        a.scale = sc;
+        a.lens_k0 = k0; a.lens_2f = two_f;
+        if (mask != nullptr) {
+            a.mask = static_cast<const char*>(mask) +
+                     b0 * mask_stride * (mask_kind == MASK_CX ? sizeof(cx<T>) : mask_kind == MASK_REAL ? sizeof(T) : 1);
+            a.mask_kind = mask_kind;
+            a.mask_beam_stride = mask_stride;
+        }
+        int rc = rows<T>(p, pre, a, nb, s);
+        if (rc) return rc;
+        LineArgs<T> c = base_args<T>(p);
+        c.in = a.out; c.out = a.out;
+        c.flags = a.flags; c.scale = sc;
+        rc = cols<T>(p, MID_NONE, c, nb, s);
+        if (rc) return rc;
+    }
+    return LP2D_OK;
+}
+
+template <typename T>
+int propagate_state(const lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
+                    cudaStream_t s) {
+    const long long plane = (long long)p->n * p->n;
+    const long long cb = chunk_beams<T>(p, batch);
+    const T sc = (T)(1.0 / (double)p->n);
+    for (long long b0 = 0; b0 < batch; b0 += cb) {
+        const long long nb = (batch - b0 < cb) ? batch - b0 : cb;
+        // rows: spectrum *= H (stored back), inverse row transform -> field buffer
+        LineArgs<T> a = base_args<T>(p);
+        a.in = static_cast<const cx<T>*>(spectrum) + b0 * plane;
+        a.out_pre = static_cast<cx<T>*>(spectrum) + b0 * plane;
+        a.out = static_cast<cx<T>*>(field) + b0 * plane;
+        a.flags = F_INVERSE; a.scale = sc; a.z = z;
+        int rc = rows<T>(p, PRE_H, a, nb, s);
+        if (rc) return rc;
+        // columns: inverse transform in place, optional |E|^2
+        LineArgs<T> c = base_args<T>(p);
+        c.in = a.out; c.out = a.out;
+        c.inten = intensity ? static_cast<T*>(intensity) + b0 * plane : nullptr;
+        c.flags = F_INVERSE; c.scale = sc;
+        rc = cols<T>(p, MID_NONE, c, nb, s);
+        if (rc) return rc;
+    }
+    return LP2D_OK;
+}
+
+template <typename T>
+int propagate_fresh(const lp2d_plan* p, const void* fin, void* fout, void* spec_out, void* intensity, void* work,
+                    long long work_bytes, long long batch, double z, cudaStream_t s) {
+    const long long plane = (long long)p->n * p->n;
+    long long cb = chunk_beams<T>(p, batch);
+    const bool via_work = (fout == nullptr);
+    if (via_work) {
+        const long long fit = work_bytes / (plane * (long long)sizeof(cx<T>));
+        if (work == nullptr || fit < 1) return fail(LP2D_EINVAL, "propagate_field: field_out is NULL and work holds less than one plane");
+        if (cb > fit) cb = fit;
+    }
+    const T sc = (T)(1.0 / (double)p->n);
+    for (long long b0 = 0; b0 < batch; b0 += cb) {
+        const long long nb = (batch - b0 < cb) ? batch - b0 : cb;
+        cx<T>* buf = via_work ? static_cast<cx<T>*>(work) : static_cast<cx<T>*>(fout) + b0 * plane;
+        // 1. forward row transform: field -> buf
+        LineArgs<T> a = base_args<T>(p);
+        a.in = static_cast<const cx<T>*>(fin) + b0 * plane;
+        a.out = buf;
+        int rc = rows<T>(p, PRE_NONE, a, nb, s);
+        if (rc) return rc;
+        // 2. fused column pass in place: FFT_y, H, inverse FFT_y (scaled 1/N)
+        LineArgs<T> c = base_args<T>(p);
+        c.in = buf; c.out = buf; c.z = z; c.scale = sc;
+        c.out_mid = spec_out ? static_cast<cx<T>*>(spec_out) + b0 * plane : nullptr;
+        rc = cols<T>(p, MID_H, c, nb, s);
+        if (rc) return rc;
+        // 3. inverse row transform (scaled 1/N): buf -> field_out and/or |E|^2
+        LineArgs<T> r = base_args<T>(p);
+        r.in = buf;
+        r.out = via_work ? nullptr : buf;
+        r.flags = F_INVERSE; r.scale = sc;
+        r.inten = intensity ? static_cast<T*>(intensity) + b0 * plane : nullptr;
+        rc = rows<T>(p, PRE_NONE, r, nb, s);
+        if (rc) return rc;
+    }
+    return LP2D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lp2d_fft2(lp2d_plan* p, const void* in, void* out, long long batch, int inverse, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (in == nullptr || out == nullptr || batch < 0) return fail(LP2D_EINVAL, "fft2: NULL pointer or negative batch");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return p->dtype == LP2D_C64
+               ? mul_fft2<float>(p, in, nullptr, out, nullptr, 0, 0, batch, inverse, PRE_NONE, 0, 0, s)
+               : mul_fft2<double>(p, in, nullptr, out, nullptr, 0, 0, batch, inverse, PRE_NONE, 0, 0, s);
+}
+
+int lp2d_propagate(lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
+                   void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (spectrum == nullptr || field == nullptr || batch < 0) return fail(LP2D_EINVAL, "propagate: NULL pointer or negative batch");
+    if (spectrum == field) return fail(LP2D_EINVAL, "propagate: spectrum and field must be distinct buffers");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, intensity, batch, z, s)
+                                : propagate_state<double>(p, spectrum, field, intensity, batch, z, s);
+}
+
+int lp2d_propagate_field(lp2d_plan* p, const void* field_in, void* field_out, void* spectrum_out, void* intensity,
+                         void* work, long long work_bytes, long long batch, double z, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (field_in == nullptr || batch < 0) return fail(LP2D_EINVAL, "propagate_field: NULL input or negative batch");
+    if (field_out == nullptr && intensity == nullptr && spectrum_out == nullptr)
+        return fail(LP2D_EINVAL, "propagate_field: no output requested");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return p->dtype == LP2D_C64
+               ? propagate_fresh<float>(p, field_in, field_out, spectrum_out, intensity, work, work_bytes, batch, z, s)
+               : propagate_fresh<double>(p, field_in, field_out, spectrum_out, intensity, work, work_bytes, batch, z, s);
+}
+
+int lp2d_lens(lp2d_plan* p, void* field, void* spectrum, long long batch, double k0, double f, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (field == nullptr || spectrum == nullptr || batch < 0) return fail(LP2D_EINVAL, "lens: NULL pointer or negative batch");
+    if (field == spectrum) return fail(LP2D_EINVAL, "lens: field and spectrum must be distinct buffers");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return p->dtype == LP2D_C64
+               ? mul_fft2<float>(p, field, field, spectrum, nullptr, 0, 0, batch, 0, PRE_LENS, k0, 2.0 * f, s)
+               : mul_fft2<double>(p, field, field, spectrum, nullptr, 0, 0, batch, 0, PRE_LENS, k0, 2.0 * f, s);
+}
+
+int lp2d_mul_fft2(lp2d_plan* p, void* data, void* other, const void* mask, int mask_kind, long long mask_beam_stride,
+                  long long batch, int inverse, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (data == nullptr || other == nullptr || batch < 0) return fail(LP2D_EINVAL, "mul_fft2: NULL pointer or negative batch");
+    if (data == other) return fail(LP2D_EINVAL, "mul_fft2: data and other must be distinct buffers");
+    if (mask != nullptr && (mask_kind < LP2D_MASK_COMPLEX || mask_kind > LP2D_MASK_U8))
+        return fail(LP2D_EINVAL, "mul_fft2: unknown mask_kind");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    void* state = mask ? data : nullptr;
+    return p->dtype == LP2D_C64
+               ? mul_fft2<float>(p, data, state, other, mask, mask_kind, mask_beam_stride, batch, inverse, PRE_NONE, 0, 0, s)
+               : mul_fft2<double>(p, data, state, other, mask, mask_kind, mask_beam_stride, batch, inverse, PRE_NONE, 0, 0, s);
+}
+
+int lp2d_intensity(lp2d_plan* p, const void* field, void* out, long long batch, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (field == nullptr || out == nullptr || batch < 0) return fail(LP2D_EINVAL, "intensity: NULL pointer or negative batch");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long n = batch * (long long)p->n * p->n;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (p->dtype == LP2D_C64)
+        intensity_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const float2*>(field), static_cast<float*>(out), n);
+    else
+        intensity_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const double2*>(field), static_cast<double*>(out), n);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "intensity launch");
+    return LP2D_OK;
+}
+
+}  // extern "C"

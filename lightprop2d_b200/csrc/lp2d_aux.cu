@@ -1,0 +1,261 @@
+// Pointwise / resampling / reduction kernels around the transform passes:
+// expand (edge-replicating pad), coarse (block mean), phase, intensity moments,
+// and the SIMT form of the mode projection / synthesis.
+#include <string>
+
+#include "../../include/lp2d.h"
+#include "dispatch.h"
+
+namespace lp2d {
+int set_error(int code, const std::string& msg);   // lp2d_api.cu
+
+// out[b][r][c] = in[b][clamp(r-pad)][clamp(c-pad)]      (beam2d.py:392-401)
+template <typename T>
+__global__ void expand_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int n_in, int n_out,
+                              long long total) {
+    const int pad = (n_out - n_in) / 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % n_out);
+        const long long rb = i / n_out;
+        const int r = (int)(rb % n_out);
+        const long long b = rb / n_out;
+        int rs = r - pad; rs = rs < 0 ? 0 : (rs >= n_in ? n_in - 1 : rs);
+        int cs = c - pad; cs = cs < 0 ? 0 : (cs >= n_in ? n_in - 1 : cs);
+        out[i] = in[(b * n_in + rs) * (long long)n_in + cs];
+    }
+}
+
+// out[b][r][c] = mean of the m x m block                  (beam2d.py:456-459)
+template <typename T>
+__global__ void coarse_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int n_in, int m,
+                              long long total) {
+    const int n_out = n_in / m;
+    const T inv = (T)1 / (T)(m * m);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % n_out);
+        const long long rb = i / n_out;
+        const int r = (int)(rb % n_out);
+        const long long b = rb / n_out;
+        const cx<T>* src = in + (b * n_in + (long long)r * m) * n_in + (long long)c * m;
+        T sx = 0, sy = 0;
+        for (int dr = 0; dr < m; ++dr)
+            for (int dc = 0; dc < m; ++dc) {
+                const cx<T> v = src[(long long)dr * n_in + dc];
+                sx += v.x; sy += v.y;
+            }
+        out[i] = mk<T>(sx * inv, sy * inv);
+    }
+}
+
+template <typename T>
+__global__ void phase_kernel(const cx<T>* __restrict__ f, T* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const cx<T> v = f[i];
+        out[i] = atan2(v.y, v.x);
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out[0..4] += [sum I, sum x I, sum y I, sum (x-xc)^2 I, sum (y-yc)^2 I],  x = (i - n/2) dL
+// (the mgrid[-n:n] * dL grids of beam2d.py:680-684, 696-702), I in the field's real type.
+template <typename T>
+__global__ void moments_kernel(const cx<T>* __restrict__ f, int n, double dL, double xc, double yc,
+                               double* __restrict__ out) {
+    double acc[5] = {0, 0, 0, 0, 0};
+    const long long total = (long long)n * n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int h = n / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % n), r = (int)(i / n);
+        const cx<T> v = f[i];
+        const double I = (double)(T)(v.x * v.x + v.y * v.y);
+        const double x = (double)(c - h) * dL, y = (double)(r - h) * dL;
+        acc[0] += I;
+        acc[1] += x * I;
+        acc[2] += y * I;
+        acc[3] += (x - xc) * (x - xc) * I;
+        acc[4] += (y - yc) * (y - yc) * I;
+    }
+    __shared__ double sm[5][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double s = warp_sum(acc[k]);
+        if (lane == 0) sm[k][w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double s = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += sm[threadIdx.x][q];
+        atomicAdd(&out[threadIdx.x], s);
+    }
+}
+
+// SIMT mode projection: coeffs[b][k] = sum_p M[k][p] * field_b[crop(p)]  (no conjugate, beam2d.py:592-600).
+// One CTA per (mode, beam); FP64 accumulation for both field types.
+template <typename T>
+__global__ void modes_project_kernel(const cx<T>* __restrict__ field, const cx<T>* __restrict__ modes,
+                                     cx<T>* __restrict__ coeffs, int n, int nb, int nmodes) {
+    const int k = blockIdx.x;
+    const long long b = blockIdx.y;
+    const int dn = (n - nb) / 2;
+    const cx<T>* mrow = modes + (long long)k * nb * nb;
+    const cx<T>* f = field + b * (long long)n * n;
+    double ax = 0, ay = 0;
+    for (int p = threadIdx.x; p < nb * nb; p += blockDim.x) {
+        const int r = p / nb, c = p % nb;
+        const cx<T> mv = mrow[p];
+        const cx<T> fv = f[(long long)(r + dn) * n + (c + dn)];
+        ax += (double)mv.x * fv.x - (double)mv.y * fv.y;
+        ay += (double)mv.x * fv.y + (double)mv.y * fv.x;
+    }
+    __shared__ double sm[2][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    ax = warp_sum(ax); ay = warp_sum(ay);
+    if (lane == 0) { sm[0][w] = ax; sm[1][w] = ay; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sx = 0, sy = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { sx += sm[0][q]; sy += sm[1][q]; }
+        coeffs[b * nmodes + k] = mk<T>((T)sx, (T)sy);
+    }
+}
+
+// SIMT mode synthesis: field_b[r][c] = sum_k coeffs[b][k] * M[k][crop^-1(r, c)], zero outside the
+// centred nb x nb window (beam2d.py:552-562, 664-666).
+template <typename T>
+__global__ void modes_synthesize_kernel(const cx<T>* __restrict__ coeffs, const cx<T>* __restrict__ modes,
+                                        cx<T>* __restrict__ field, int n, int nb, int nmodes) {
+    const long long b = blockIdx.y;
+    const int dn = (n - nb) / 2;
+    const int nt = n - dn;
+    const long long total = (long long)n * n;
+    const cx<T>* cb = coeffs + b * nmodes;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % n), r = (int)(i / n);
+        double ax = 0, ay = 0;
+        if (r >= dn && r < nt && c >= dn && c < nt) {
+            const long long p = (long long)(r - dn) * nb + (c - dn);
+            for (int k = 0; k < nmodes; ++k) {
+                const cx<T> mv = modes[(long long)k * nb * nb + p];
+                const cx<T> cv = cb[k];
+                ax += (double)mv.x * cv.x - (double)mv.y * cv.y;
+                ay += (double)mv.x * cv.y + (double)mv.y * cv.x;
+            }
+        }
+        field[b * total + i] = mk<T>((T)ax, (T)ay);
+    }
+}
+
+static unsigned grid_for(long long total, int threads) {
+    long long blocks = (total + threads - 1) / threads;
+    const long long cap = 148ll * 32;
+    return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+static int done(const char* what) {
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return LP2D_OK;
+}
+}  // namespace lp2d
+
+using namespace lp2d;
+
+#define LP2D_DTYPE_OK(d) ((d) == LP2D_C64 || (d) == LP2D_C128)
+
+extern "C" {
+
+int lp2d_expand(int dtype, const void* in, void* out, int n_in, int n_out, long long batch, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || in == nullptr || out == nullptr || n_in <= 0 || n_out < n_in || ((n_out - n_in) & 1) || batch < 0)
+        return set_error(LP2D_EINVAL, "expand: bad arguments (n_out - n_in must be even and >= 0)");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long total = batch * (long long)n_out * n_out;
+    if (dtype == LP2D_C64)
+        expand_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float2*)in, (float2*)out, n_in, n_out, total);
+    else
+        expand_kernel<double><<<grid_for(total, 256), 256, 0, s>>>((const double2*)in, (double2*)out, n_in, n_out, total);
+    return done("expand launch");
+}
+
+int lp2d_coarse(int dtype, const void* in, void* out, int n_in, int m, long long batch, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || in == nullptr || out == nullptr || n_in <= 0 || m <= 0 || n_in % m != 0 || batch < 0)
+        return set_error(LP2D_EINVAL, "coarse: bad arguments (mean_order must divide npoints)");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long total = batch * (long long)(n_in / m) * (n_in / m);
+    if (dtype == LP2D_C64)
+        coarse_kernel<float><<<grid_for(total, 256), 256, 0, s>>>((const float2*)in, (float2*)out, n_in, m, total);
+    else
+        coarse_kernel<double><<<grid_for(total, 256), 256, 0, s>>>((const double2*)in, (double2*)out, n_in, m, total);
+    return done("coarse launch");
+}
+
+int lp2d_phase(int dtype, const void* field, void* out, long long count, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || field == nullptr || out == nullptr || count < 0)
+        return set_error(LP2D_EINVAL, "phase: bad arguments");
+    if (count == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == LP2D_C64)
+        phase_kernel<float><<<grid_for(count, 256), 256, 0, s>>>((const float2*)field, (float*)out, count);
+    else
+        phase_kernel<double><<<grid_for(count, 256), 256, 0, s>>>((const double2*)field, (double*)out, count);
+    return done("phase launch");
+}
+
+int lp2d_moments(int dtype, const void* field, int n, double dL, double xc, double yc, double* out5, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || field == nullptr || out5 == nullptr || n <= 0)
+        return set_error(LP2D_EINVAL, "moments: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(out5, 0, 5 * sizeof(double), s);
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("moments memset: ") + cudaGetErrorString(e));
+    const unsigned grid = grid_for((long long)n * n, 256 * 8);
+    if (dtype == LP2D_C64)
+        moments_kernel<float><<<grid, 256, 0, s>>>((const float2*)field, n, dL, xc, yc, out5);
+    else
+        moments_kernel<double><<<grid, 256, 0, s>>>((const double2*)field, n, dL, xc, yc, out5);
+    return done("moments launch");
+}
+
+int lp2d_modes_project(int dtype, const void* field, const void* modes, void* coeffs, int n, int nb, int nmodes,
+                       long long batch, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || field == nullptr || modes == nullptr || coeffs == nullptr || n <= 0 || nb <= 0 || nb > n ||
+        nmodes <= 0 || batch < 0 || batch > 65535)
+        return set_error(LP2D_EINVAL, "modes_project: bad arguments");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)nmodes, (unsigned)batch);
+    if (dtype == LP2D_C64)
+        modes_project_kernel<float><<<grid, 256, 0, s>>>((const float2*)field, (const float2*)modes, (float2*)coeffs, n, nb, nmodes);
+    else
+        modes_project_kernel<double><<<grid, 256, 0, s>>>((const double2*)field, (const double2*)modes, (double2*)coeffs, n, nb, nmodes);
+    return done("modes_project launch");
+}
+
+int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void* field, int n, int nb, int nmodes,
+                          long long batch, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || field == nullptr || modes == nullptr || coeffs == nullptr || n <= 0 || nb <= 0 || nb > n ||
+        nmodes <= 0 || batch < 0 || batch > 65535)
+        return set_error(LP2D_EINVAL, "modes_synthesize: bad arguments");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid(grid_for((long long)n * n, 256), (unsigned)batch);
+    if (dtype == LP2D_C64)
+        modes_synthesize_kernel<float><<<grid, 256, 0, s>>>((const float2*)coeffs, (const float2*)modes, (float2*)field, n, nb, nmodes);
+    else
+        modes_synthesize_kernel<double><<<grid, 256, 0, s>>>((const double2*)coeffs, (const double2*)modes, (double2*)field, n, nb, nmodes);
+    return done("modes_synthesize launch");
+}
+
+}  // extern "C"

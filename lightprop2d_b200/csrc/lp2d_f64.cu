@@ -1,0 +1,20 @@
+// complex128 kernel set: (N, E, rows per CTA, columns per CTA)
+#include "sizes.cuh"
+
+namespace lp2d {
+static const SizeOps<double> kOpsF64[] = {
+    Ops<double, 16, 8, 64, 8>::entry(),
+    Ops<double, 32, 8, 32, 8>::entry(),
+    Ops<double, 64, 8, 16, 8>::entry(),
+    Ops<double, 128, 8, 8, 8>::entry(),
+    Ops<double, 256, 8, 8, 8>::entry(),
+    Ops<double, 512, 8, 4, 4>::entry(),
+    Ops<double, 1024, 8, 2, 4>::entry(),
+    Ops<double, 2048, 8, 1, 2>::entry(),
+    Ops<double, 4096, 8, 1, 1>::entry(),
+};
+const SizeOps<double>* find_ops_f64(int n) {
+    for (const auto& o : kOpsF64) if (o.n == n) return &o;
+    return nullptr;
+}
+}  // namespace lp2d
