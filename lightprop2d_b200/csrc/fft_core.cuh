@@ -132,7 +132,7 @@ struct LinePlan {
     __host__ __device__ static constexpr int tw_size() { return tw_offset(npass()); }
     // shared-memory padding: one extra slot every PADSTEP samples so that the
     // stride-R scatter of pass 0 (Ns = 1) spreads over the banks
-    static constexpr int PADSTEP = (radix(0) < 16 ? 16 : radix(0));
+    static constexpr int PADSTEP = (radix(0) < 4 ? 4 : radix(0));
     __host__ __device__ static constexpr int pad(int i) { return i + i / PADSTEP; }
     static constexpr int LINE_SLOTS = N + N / PADSTEP;      // padded samples per line
 };
