@@ -105,6 +105,23 @@ LP2D_API int lp2d_lens(lp2d_plan* plan, void* field, void* spectrum, long long b
 LP2D_API int lp2d_mul_fft2(lp2d_plan* plan, void* data, void* other, const void* mask, int mask_kind,
                   long long mask_beam_stride, long long batch, int inverse, void* stream);
 
+/* One pass of the decomposition, for callers that interleave their own step between
+ * the row and the column pass (the slab-decomposed grid exchanges tiles in between)
+ * and for per-kernel timing.  axis: rows are the contiguous axis.
+ *   LP2D_OP_FFT        out = (i)fft along the axis (inverse scaled by 1/n)
+ *   LP2D_OP_H_FFT      rows only: data *= H(z); out_state (may be NULL) = data*H;
+ *                      out = (i)fft of that along the rows
+ *   LP2D_OP_FFT_H_IFFT columns only: fft, *= H(z), out_state (may be NULL) = that,
+ *                      out = ifft (scaled by 1/n)
+ * `intensity` (may be NULL) = |out|^2.  out may be NULL when only intensity is wanted. */
+#define LP2D_AXIS_ROWS 0
+#define LP2D_AXIS_COLS 1
+#define LP2D_OP_FFT 0
+#define LP2D_OP_H_FFT 1
+#define LP2D_OP_FFT_H_IFFT 2
+LP2D_API int lp2d_pass(lp2d_plan* plan, int axis, int op, const void* in, void* out, void* out_state,
+              void* intensity, long long batch, int inverse, double z, void* stream);
+
 /* iprofile (beam2d.py:717): out = |field|^2 (float for complex64, double for complex128). */
 LP2D_API int lp2d_intensity(lp2d_plan* plan, const void* field, void* out, long long batch, void* stream);
 

@@ -12,6 +12,8 @@ _LIB_PATH = os.path.join(_HERE, "liblp2d.so")
 
 C64, C128 = 0, 1
 MASK_COMPLEX, MASK_REAL, MASK_U8 = 1, 2, 3
+AXIS_ROWS, AXIS_COLS = 0, 1
+OP_FFT, OP_H_FFT, OP_FFT_H_IFFT = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/lp2d.h one to one
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
@@ -29,6 +31,7 @@ SIGNATURES = {
     "lp2d_propagate_field": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _d, _vp]),
     "lp2d_lens": (_i, [_vp, _vp, _vp, _ll, _d, _d, _vp]),
     "lp2d_mul_fft2": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _vp]),
+    "lp2d_pass": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _i, _d, _vp]),
     "lp2d_intensity": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "lp2d_expand": (_i, [_i, _vp, _vp, _i, _i, _ll, _vp]),
     "lp2d_coarse": (_i, [_i, _vp, _vp, _i, _i, _ll, _vp]),

@@ -359,6 +359,36 @@ int lp2d_mul_fft2(lp2d_plan* p, void* data, void* other, const void* mask, int m
                : mul_fft2<double>(p, data, state, other, mask, mask_kind, mask_beam_stride, batch, inverse, PRE_NONE, 0, 0, s);
 }
 
+int lp2d_pass(lp2d_plan* p, int axis, int op, const void* in, void* out, void* out_state, void* intensity,
+              long long batch, int inverse, double z, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (in == nullptr || batch < 0 || (axis != LP2D_AXIS_ROWS && axis != LP2D_AXIS_COLS))
+        return fail(LP2D_EINVAL, "pass: bad arguments");
+    if (op < LP2D_OP_FFT || op > LP2D_OP_FFT_H_IFFT) return fail(LP2D_EINVAL, "pass: unknown op");
+    if (axis == LP2D_AXIS_ROWS && op == LP2D_OP_FFT_H_IFFT) return fail(LP2D_EUNSUPPORTED, "pass: the fused FFT-H-IFFT pass exists for columns only");
+    if (axis == LP2D_AXIS_COLS && op == LP2D_OP_H_FFT) return fail(LP2D_EUNSUPPORTED, "pass: the H-then-transform pass exists for rows only");
+    if (batch == 0) return LP2D_OK;
+    if (batch * (long long)p->n > 0x7fffffffll) return fail(LP2D_EINVAL, "pass: batch too large for one launch");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double sc = (inverse || op == LP2D_OP_FFT_H_IFFT) ? 1.0 / (double)p->n : 1.0;
+#define LP2D_PASS_BODY(T)                                                                        \
+    {                                                                                            \
+        LineArgs<T> a = base_args<T>(p);                                                         \
+        a.in = static_cast<const cx<T>*>(in);                                                    \
+        a.out = static_cast<cx<T>*>(out);                                                        \
+        if (op == LP2D_OP_FFT_H_IFFT) a.out_mid = static_cast<cx<T>*>(out_state);                \
+        else a.out_pre = static_cast<cx<T>*>(out_state);                                         \
+        a.inten = static_cast<T*>(intensity);                                                    \
+        a.flags = inverse ? F_INVERSE : 0;                                                       \
+        a.scale = (T)sc;                                                                         \
+        a.z = z;                                                                                 \
+        return axis == LP2D_AXIS_ROWS ? rows<T>(p, op == LP2D_OP_H_FFT ? PRE_H : PRE_NONE, a, batch, s) \
+                                      : cols<T>(p, op == LP2D_OP_FFT_H_IFFT ? MID_H : MID_NONE, a, batch, s); \
+    }
+    if (p->dtype == LP2D_C64) LP2D_PASS_BODY(float) else LP2D_PASS_BODY(double)
+#undef LP2D_PASS_BODY
+}
+
 int lp2d_intensity(lp2d_plan* p, const void* field, void* out, long long batch, void* stream) {
     LP2D_CHECK_PLAN(p);
     if (field == nullptr || out == nullptr || batch < 0) return fail(LP2D_EINVAL, "intensity: NULL pointer or negative batch");

@@ -1,0 +1,350 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes) behind Beam2D, against
+(a) outputs of the reference itself (tests/golden), (b) the numpy oracle on identical seeded
+inputs, (c) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): relative L2 on field / iprofile <= 1e-5 (complex64), <= 1e-12
+(complex128); grids bit exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+import lightprop2d_b200 as lp  # noqa: E402
+from lightprop2d_b200 import Beam2D, _lib, um, nm, mm  # noqa: E402
+from lightprop2d_b200.ensemble import EnsemblePropagator  # noqa: E402
+from oracle import beam_oracle as orc  # noqa: E402
+
+TOL = {64: 1e-5, 128: 1e-12}
+CT = {64: np.complex64, 128: np.complex128}
+BITS = [64, 128]
+
+
+# ------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_readme_example(bits):
+    g = golden(f"readme_c{bits}")
+    np.random.seed(0)
+    b = Beam2D(200 * um, 256, 632 * nm, init_field_gen=lp.random_round_hole,
+               init_gen_args=(25 * um,), complex_bits=bits)
+    i0 = b.iprofile
+    assert i0.dtype == (np.float32 if bits == 64 else np.float64)
+    b.propagate(100 * um)
+    assert b.field.dtype == CT[bits]
+    assert rel_l2(b.field, g["field"]) <= TOL[bits]
+    assert abs(b.iprofile.sum() - g["iprofile_sum"][1]) <= 10 * TOL[bits] * g["iprofile_sum"][1]
+    assert abs(i0.sum() - g["iprofile_sum"][0]) <= 10 * TOL[bits] * g["iprofile_sum"][0]
+    assert b.z == g["z"]
+    assert abs(b.spectrum.sum() - g["spectrum_sum"]) <= 1e3 * TOL[bits] * abs(g["spectrum_sum"])
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_lens_sweep(bits):
+    g = golden(f"lens_sweep_c{bits}")
+    b = Beam2D(3 * mm, 128, 632 * nm, init_field_gen=lp.gaussian_beam, init_gen_args=(1., 0.03),
+               complex_bits=bits)
+    assert rel_l2(b.field, g["field0"]) <= TOL[bits]
+    b.lens(0.5)
+    assert rel_l2(b.field, g["field_lens"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum_lens"]) <= TOL[bits]
+    for _ in range(3):
+        b.propagate(0.02)
+    b.propagate(-0.013)
+    assert rel_l2(b.field, g["field"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum"]) <= TOL[bits]
+    assert b.z == g["z"]
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_filters(bits):
+    g = golden(f"filters_c{bits}")
+    np.random.seed(3)
+    b = Beam2D(200 * um, 64, 632 * nm, init_field_gen=lp.random_wave, complex_bits=bits)
+    b.coordinate_filter(f_gen=lp.round_hole, fargs=(60 * um,))            # bool mask
+    assert rel_l2(b.field, g["field_a"]) <= TOL[bits]
+    mask = g["mask"]
+    b.coordinate_filter(f_init=mask.astype(CT[bits]))                      # complex mask
+    assert rel_l2(b.field, g["field_b"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum_b"]) <= TOL[bits]
+    b.spectral_filter(f_gen=lp.rectangle_hole, fargs=(4000., 2500.))       # bool mask on (Kx, Ky)
+    assert rel_l2(b.field, g["field_c"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum_c"]) <= TOL[bits]
+    b.spectral_filter(f_init=np.abs(mask).astype(np.float64))              # real mask
+    assert rel_l2(b.field, g["field_d"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum_d"]) <= TOL[bits]
+    with pytest.raises(AssertionError):
+        b.coordinate_filter(f_gen=3)
+    with pytest.raises(AssertionError):
+        b.coordinate_filter(f_init=[1, 2])
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_expand_coarse(bits):
+    g = golden(f"resample_c{bits}")
+    np.random.seed(11)
+    b = Beam2D(200 * um, 64, 632 * nm, init_field_gen=lp.random_round_hole_phase,
+               init_gen_args=(50 * um,), complex_bits=bits)
+    b.expand(400 * um)
+    assert b.npoints == int(g["n_e"]) and np.array_equal(b.X, g["X_e"])
+    assert rel_l2(b.field, g["field_e"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum_e"]) <= TOL[bits]
+    b.coarse(2)
+    assert b.npoints == int(g["n_c"])
+    assert rel_l2(b.field, g["field_c"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum_c"]) <= TOL[bits]
+    b.propagate(30 * um)
+    with pytest.raises(NotImplementedError):      # 82 points: not a power of two -> loud, no fallback
+        b.expand(520 * um)
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_observables(bits):
+    g = golden(f"observables_c{bits}")
+    b = Beam2D(3 * mm, 128, 632 * nm, init_field_gen=lp.gaussian_beam,
+               init_gen_args=(1., 0.03, 0.011, -0.007), complex_bits=bits)
+    assert np.array_equal(b.X, g["X"])
+    b.lens(2.)
+    b.propagate(0.7)
+    assert rel_l2(b.field, g["field"]) <= TOL[bits]
+    assert b.iprofile.dtype == g["iprofile"].dtype
+    assert rel_l2(b.iprofile, g["iprofile"]) <= TOL[bits]
+    ph = b.phiprofile
+    d = np.angle(np.exp(1j * (ph - g["phiprofile"])))          # compare modulo 2 pi
+    w = g["iprofile"] > 1e-6 * g["iprofile"].max()
+    assert np.max(np.abs(d[w])) < (1e-2 if bits == 64 else 1e-8)
+    rt = 1e-5 if bits == 64 else 1e-11
+    xc, yc, nxc, nyc = b.centroid
+    assert np.allclose([xc, yc], g["centroid"], rtol=rt)
+    assert [nxc, nyc] == list(g["centroid_idx"])
+    assert np.allclose(b.D4sigma, g["d4sigma"], rtol=rt)
+    assert np.allclose(b.centroid_intensity, g["centroid_intensity"], rtol=10 * rt)
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_modes(bits):
+    g = golden(f"modes_c{bits}")
+    np.random.seed(2)
+    b = Beam2D(200 * um, 64, 632 * nm, init_field_gen=lp.random_wave, complex_bits=bits)
+    c = b.deconstruct_by_modes(g["modes"])
+    assert rel_l2(c, g["coeffs"]) <= TOL[bits]
+    b.construct_by_modes(g["modes"], c)
+    assert rel_l2(b.field, g["field"]) <= TOL[bits]
+    assert rel_l2(b.spectrum, g["spectrum"]) <= TOL[bits]
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_batched(bits):
+    g = golden(f"batched_c{bits}")
+    b = Beam2D(200 * um, 64, 632 * nm, init_field=g["field0"].astype(CT[bits]), complex_bits=bits)
+    b.lens(0.01)
+    b.propagate(50 * um)
+    assert b.field.shape == (3, 64, 64)
+    assert rel_l2(b.field, g["field"]) <= TOL[bits]
+    assert rel_l2(b.iprofile, g["iprofile"]) <= TOL[bits]
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_gauss_axis(bits):
+    """The one analytic law the reference's scripts check: on-axis I(z) of a Gaussian beam."""
+    g = golden(f"gauss_axis_c{bits}")
+    area, n, wl, R, dz = g["params"]
+    n = int(n)
+    b = Beam2D(area, n, wl, init_field_gen=lp.gaussian_beam, init_gen_args=(1., R), complex_bits=bits)
+    i0 = []
+    for _ in range(40):
+        b.propagate(dz)
+        i0.append(b.iprofile[n // 2, n // 2])
+    i0 = np.array(i0)
+    assert np.allclose(i0, g["i0"], rtol=2e-5 if bits == 64 else 1e-11)
+    zn = 2 * (np.arange(1, 41) * dz) / (2 * np.pi * (1 / wl) * R ** 2)
+    assert np.max(np.abs(i0 * (1 + zn ** 2) - 1)) < (1e-5 if bits == 64 else 1e-8)
+
+
+def test_golden_update_obj():
+    g = golden("update_obj")
+    np.random.seed(7)
+    b = Beam2D(200 * um, 64, 632 * nm, init_field_gen=lp.random_wave)
+    b.propagate(10 * um)
+    b._update_obj(g["field_in"].copy())
+    assert b.z == g["z"][0]
+    b.propagate(20 * um)
+    assert b.z == g["z"][1]
+    assert rel_l2(b.field, g["field"]) <= TOL[128]
+    assert rel_l2(b.spectrum, g["spectrum"]) <= TOL[128]
+    assert repr(b) == str(g["repr"])
+
+
+# --------------------------------------------------------------- oracle, seeded inputs
+@pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("seed", range(8))
+def test_config1_readme_seeds(bits, seed):
+    """BASELINE configs[0] for seeds 0..7."""
+    np.random.seed(seed)
+    b = Beam2D(200 * um, 256, 632 * nm, init_field_gen=lp.random_round_hole, init_gen_args=(25 * um,),
+               complex_bits=bits)
+    np.random.seed(seed)
+    o = orc.OracleBeam(200 * um, 256, 632 * nm, init_field_gen=lp.random_round_hole,
+                       init_gen_args=(25 * um,), complex_bits=bits)
+    assert np.array_equal(b.X, o.X) and np.array_equal(b.Kx, o.Kx) and np.array_equal(b.Kz, o.Kz)
+    b.propagate(100 * um); o.propagate(100 * um)
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+    assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits]
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+
+
+@pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 512, 1024, 2048])
+def test_oracle_chain_sizes(bits, n):
+    """lens -> several propagate steps (both signs) -> filters, every supported size class."""
+    rng = np.random.default_rng(1000 + n)
+    f0 = (rng.uniform(size=(n, n)) * np.exp(2j * np.pi * rng.uniform(size=(n, n)))).astype(CT[bits])
+    area, wl = 4e-1 * n / 1024, 532e-7
+    b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    for f, z in ((0.1, 0.02), (-0.3, 10.0), (5.0, -0.5)):
+        b.lens(f); o.lens(f)
+        b.propagate(z); o.propagate(z)
+        assert rel_l2(b.field, o.field) <= TOL[bits], (f, z)
+        assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits], (f, z)
+        assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits], (f, z)
+    b.propagate(0); o.propagate(0)
+    assert b.z == o.z
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_evanescent_region_passes_unattenuated(bits):
+    """k0 < |K| somewhere: sqrt gives NaN -> 0 -> H = 1 (beam2d.py:307-308), reproduced."""
+    n, area, wl = 64, 0.05, 2e-3
+    rng = np.random.default_rng(5)
+    f0 = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(CT[bits])
+    b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    assert (o.Kz == 0).sum() > 100
+    b.propagate(0.37); o.propagate(0.37)
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+
+
+def test_constructor_errors_and_dtypes():
+    with pytest.raises(ValueError, match="Init field data is None"):
+        Beam2D(200 * um, 64, 632 * nm)
+    with pytest.raises(NotImplementedError):
+        Beam2D(200 * um, 48, 632 * nm, init_field_gen=lp.plane_wave)
+    with pytest.raises(ValueError):
+        Beam2D(200 * um, 64, 632 * nm, init_field=np.ones((32, 32)))
+    with pytest.raises(ValueError, match="Unknown type"):
+        Beam2D(200 * um, 64, 632 * nm, init_field=[[1.0]])
+    b = Beam2D(200 * um, 64, 632 * nm, init_field_gen=lp.rectangle_hole, init_gen_args=(1e-2, 5e-3),
+               complex_bits=64, use_gpu=True, numpy_output=False)
+    assert isinstance(b.field, torch.Tensor) and b.field.is_cuda and b.field.dtype == torch.complex64
+    assert isinstance(b.iprofile, torch.Tensor) and b.iprofile.dtype == torch.float32
+    b2 = Beam2D(200 * um, 64, 632 * nm, init_field=b.field, init_spectrum=b.spectrum, complex_bits=64)
+    assert isinstance(b2.field, np.ndarray) and rel_l2(b2.spectrum, b._np(b.spectrum)) == 0
+    with pytest.raises(NotImplementedError):
+        b.crop(100 * um)
+    with pytest.raises(NotImplementedError):
+        b.lens_image(1., 1., 1.)
+
+
+# ----------------------------------------------- full-size properties (configs[1], [2])
+@pytest.mark.parametrize("bits,n", [(128, 1024), (128, 4096), (64, 4096), (64, 8192)])
+def test_full_size_properties(bits, n):
+    """configs[1] sizes: |H| = 1 conserves sum(iprofile); propagate(z1); propagate(z2) == propagate(z1+z2);
+    propagate(z); propagate(-z) == identity; Parseval between field and spectrum."""
+    tol = 50 * TOL[bits]
+    area, wl = 4e-1, 532e-7
+    b = Beam2D(area, n, wl, init_field_gen=lp.rectangle_hole, init_gen_args=(2e-1, 1e-1),
+               complex_bits=bits, use_gpu=True, numpy_output=False)
+    f0 = b.field.clone()
+    e0 = float(b.iprofile.sum(dtype=torch.float64))
+    pars = float((b.spectrum.abs().to(torch.float64) ** 2).sum()) / (n * n)
+    assert abs(pars - e0) <= tol * e0
+    b.lens(0.3)
+    b.propagate(0.7)
+    assert abs(float(b.iprofile.sum(dtype=torch.float64)) - e0) <= tol * e0
+    f1 = b.field.clone()
+    b.propagate(0.5)
+    b.propagate(-1.2)
+    c = Beam2D(area, n, wl, init_field=f0, complex_bits=bits, use_gpu=True, numpy_output=False)
+    c.lens(0.3)
+    # b is now at z = 0 again: back to the field right after the lens
+    d = (b.field - c.field).abs().to(torch.float64).pow(2).sum().sqrt() / c.field.abs().to(torch.float64).pow(2).sum().sqrt()
+    assert float(d) <= tol
+    c.propagate(0.3); c.propagate(0.4)
+    d = (c.field - f1).abs().to(torch.float64).pow(2).sum().sqrt() / f1.abs().to(torch.float64).pow(2).sum().sqrt()
+    assert float(d) <= tol
+    assert abs(b.z) < 1e-12 and abs(c.z - 0.7) < 1e-12
+
+
+@pytest.mark.parametrize("bits", BITS)
+def test_linearity_and_batch_equals_loop(bits):
+    n, B = 512, 5
+    rng = np.random.default_rng(9)
+    f = (rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))).astype(CT[bits])
+    b = Beam2D(4e-1, n, 532e-7, init_field=f.copy(), complex_bits=bits)
+    b.propagate(3.0)
+    out = b.field
+    for k in (0, B - 1):
+        s = Beam2D(4e-1, n, 532e-7, init_field=f[k].copy(), complex_bits=bits)
+        s.propagate(3.0)
+        assert np.array_equal(s.field, out[k])             # batched == per-beam, bit for bit
+    lin = Beam2D(4e-1, n, 532e-7, init_field=(2 * f[0] - 3j * f[1]).astype(CT[bits]), complex_bits=bits)
+    lin.propagate(3.0)
+    assert rel_l2(lin.field, 2 * out[0] - 3j * out[1]) <= 20 * TOL[bits]
+
+
+def test_config3_ensemble_subset_parity():
+    """configs[2]: 64-beam subset of the 512^2 complex64 ensemble, host RNG, fft2 -> propagate -> iprofile."""
+    n, B, z = 512, 64, 100 * um
+    area, wl = 400 * um, 632 * nm
+    rng = np.random.default_rng(123)
+    x = np.arange(-n // 2, n // 2) * (area / n)
+    hole = lp.round_hole(x, x.reshape(-1, 1), 100 * um)
+    amp = rng.uniform(size=(B, n, n)) * hole
+    ph = np.exp(2j * np.pi * rng.uniform(size=(B, n, n)))
+    fields = (amp * ph).astype(np.complex64)
+    prop = EnsemblePropagator(area, n, wl, complex_bits=64)
+    dev = torch.from_numpy(fields).cuda()
+    got = prop.intensity(dev, z).cpu().numpy()
+    got_e2e = prop.intensity_from_host(torch.from_numpy(fields).pin_memory(), z, chunk=24)
+    torch.cuda.synchronize()
+    fld = prop.field(dev, z).cpu().numpy()
+    for k in range(0, B, 7):
+        o = orc.OracleBeam(area, n, wl, init_field=fields[k].copy(), complex_bits=64)
+        o.propagate(z)
+        assert rel_l2(got[k], o.iprofile) <= TOL[64]
+        assert rel_l2(fld[k], o.field) <= TOL[64]
+    assert np.array_equal(got_e2e.numpy(), got)
+    # energy conservation for every beam
+    e_in = (np.abs(fields.astype(np.complex128)) ** 2).sum((1, 2))
+    assert np.allclose(got.astype(np.float64).sum((1, 2)), e_in, rtol=1e-5)
+
+
+# -------------------------------------------------------------- raw C ABI entry points
+@pytest.mark.parametrize("bits", BITS)
+def test_cabi_passes_compose_to_fft2(bits):
+    n, B = 256, 3
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    f = (rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))).astype(CT[bits])
+    b = Beam2D(200 * um, n, 632 * nm, init_field=f.copy(), complex_bits=bits, use_gpu=True)
+    plan = b._plan.handle
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x = torch.from_numpy(f).cuda()
+    t1, t2, t3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    n0 = _lib.launch_count()
+    assert lib.lp2d_pass(plan, _lib.AXIS_ROWS, _lib.OP_FFT, x.data_ptr(), t1.data_ptr(), None, None, B, 0, 0.0, st) == 0
+    assert lib.lp2d_pass(plan, _lib.AXIS_COLS, _lib.OP_FFT, t1.data_ptr(), t2.data_ptr(), None, None, B, 0, 0.0, st) == 0
+    assert _lib.launch_count() == n0 + 2
+    assert rel_l2(t2.cpu().numpy(), np.fft.fft2(f)) <= TOL[bits]
+    assert lib.lp2d_fft2(plan, t2.data_ptr(), t3.data_ptr(), B, 1, st) == 0
+    assert rel_l2(t3.cpu().numpy(), f) <= TOL[bits]
+    assert lib.lp2d_fft2(plan, t3.data_ptr(), t3.data_ptr(), B, 0, st) == 0      # in place
+    assert rel_l2(t3.cpu().numpy(), np.fft.fft2(f)) <= TOL[bits]
+    assert lib.lp2d_fft2(plan, x.data_ptr(), t1.data_ptr(), 0, 0, st) == 0         # empty batch
+    assert lib.lp2d_propagate(plan, x.data_ptr(), x.data_ptr(), None, B, 1.0, st) == 1
+    assert lib.lp2d_pass(plan, _lib.AXIS_ROWS, _lib.OP_FFT_H_IFFT, x.data_ptr(), t1.data_ptr(), None, None, B, 0, 1.0, st) == 2
