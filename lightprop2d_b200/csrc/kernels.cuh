@@ -25,7 +25,16 @@ namespace lp2d {
 enum { AX_ROW = 0, AX_COL = 1 };
 enum { PRE_NONE = 0, PRE_LENS = 1, PRE_H = 2 };
 enum { MID_NONE = 0, MID_H = 1 };
-enum { F_INVERSE = 1 };
+enum { F_INVERSE = 1,
+       F_IN_STREAM = 2,     // input is read once: evict-first loads
+       F_OUT_STREAM = 4,    // output is not re-read soon: evict-first stores
+       F_STATE_STREAM = 8   // same for out_pre / out_mid
+};
+
+// cache-policy aware accessors: streaming data must not push the inter-pass
+// intermediate out of L2
+template <typename C> __device__ __forceinline__ C ld_cx(const C* p, bool stream) { return stream ? __ldcs(p) : *p; }
+template <typename C> __device__ __forceinline__ void st_cx(C* p, C v, bool stream) { if (stream) __stcs(p, v); else *p = v; }
 enum { MASK_NONE = 0, MASK_CX = 1, MASK_REAL = 2, MASK_U8 = 3 };
 
 template <typename T>
@@ -46,7 +55,10 @@ struct LineArgs {
     T scale;                // applied to the output of the transform
     long long beam_stride;  // samples between consecutive beams (N*N)
     long long mask_beam_stride;  // 0: one mask for every beam
-    int nlines;             // rows: beams*N; columns: beams*N/W tiles
+    int nlines;             // lines (rows) or column tiles in ONE group
+    int groups;             // beam groups a CTA walks over (>= 1)
+    long long group_beams;  // beams per group
+    long long nbeams;       // beams in the launch (the last group may be partial)
     int mask_kind;
     int flags;
 };
@@ -97,7 +109,7 @@ __device__ __forceinline__ cx<T> lens_factor(double x2_i, double y2_j, double k0
 }
 
 // ------------------------------------------------------------------ configuration
-template <typename T, int N, int E, int AXIS, int W>
+template <typename T, int N, int E, int AXIS, int W, int PRE = PRE_NONE>
 struct KCfg {
     using LP = LinePlan<N, E>;
     static constexpr int TPL = LP::TPL;
@@ -107,15 +119,29 @@ struct KCfg {
     static constexpr int S128 = 128 / (int)sizeof(cx<T>);          // samples per 128 B
     static constexpr int RES = (AXIS == AX_COL) ? (W >= S128 ? 1 : S128 / W) : (TPL < S128 ? TPL : 0);
     static constexpr int LS = LP::LINE_SLOTS + ((RES - LP::LINE_SLOTS % S128) + S128) % S128;
-    static constexpr size_t SMEM = (LP::npass() > 1) ? (size_t)W * LS * sizeof(cx<T>) : 0;
+    static constexpr size_t SMEM_X = (LP::npass() > 1) ? (size_t)W * LS * sizeof(cx<T>) : 0;   // exchange
+    // PRE_H keeps the transfer function of the CTA's W lines in shared memory so that it is
+    // computed once and reused for every beam group the CTA walks over
+    static constexpr size_t SMEM_H = (PRE == PRE_H) ? (size_t)W * N * sizeof(cx<T>) : 0;
+    static constexpr size_t SMEM = SMEM_X + SMEM_H;
+    // resident CTAs per SM the register allocation should allow: data registers are
+    // 2*E*sizeof(T)/4, the butterflies need about as many again
+    static constexpr int REGS_EST = 4 * E * (int)sizeof(T) / 4;
+    static constexpr int MINB_R = 65536 / (THREADS * REGS_EST) < 1 ? 1 : 65536 / (THREADS * REGS_EST);
+    static constexpr int MINB_S = SMEM == 0 ? 32 : (int)((227 * 1024) / (SMEM + 1024)) < 1 ? 1 : (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr int MINB_T = 2048 / THREADS < 1 ? 1 : 2048 / THREADS;
+    static constexpr int MINB = MINB_R < MINB_S ? (MINB_R < MINB_T ? MINB_R : MINB_T) : (MINB_S < MINB_T ? MINB_S : MINB_T);
     static_assert(THREADS <= 1024, "block too large");
     static_assert(SYNC != SYNC_NAMED || (W <= 15 && TPL % 32 == 0), "named barriers");
 };
 
+// One CTA: W lines (rows, or a tile of W adjacent columns).  The batch is seen as p.groups
+// slabs of (p.nlines lines) each; the CTA handles its lines in every slab, so per-line
+// constants (the transfer function) are built once and reused across beams.
 template <typename T, int N, int E, int AXIS, int W, int PRE, int MID>
-__global__ void __launch_bounds__(KCfg<T, N, E, AXIS, W>::THREADS)
+__global__ void __launch_bounds__(KCfg<T, N, E, AXIS, W, PRE>::THREADS, KCfg<T, N, E, AXIS, W, PRE>::MINB)
 line_kernel(const LineArgs<T> p) {
-    using K = KCfg<T, N, E, AXIS, W>;
+    using K = KCfg<T, N, E, AXIS, W, PRE>;
     constexpr int TPL = K::TPL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
@@ -126,124 +152,142 @@ line_kernel(const LineArgs<T> p) {
     cx<T>* sline = smem + l * K::LS;
 
     // which line of which beam; "fixed" is the grid index that is constant along the line
-    long long base;
+    long long base, mbase, beam;
     int fixed;
-    bool active;
-    long long mbase = 0;
+    bool in_range;
     if constexpr (AXIS == AX_ROW) {
         const long long line = (long long)blockIdx.x * W + l;
-        active = line < p.nlines;
-        const long long beam = line / N;
+        in_range = line < p.nlines;
+        beam = line / N;
         fixed = (int)(line % N);                              // row j
         base = beam * p.beam_stride + (long long)fixed * N;
         mbase = beam * p.mask_beam_stride + (long long)fixed * N;
     } else {
         constexpr int TILES = N / W;
         const long long tile = blockIdx.x;
-        active = tile < p.nlines;
-        const long long beam = tile / TILES;
+        in_range = tile < p.nlines;
+        beam = tile / TILES;
         fixed = (int)(tile % TILES) * W + l;                  // column i
         base = beam * p.beam_stride + fixed;
         mbase = beam * p.mask_beam_stride + fixed;
     }
     constexpr long long STRIDE = (AXIS == AX_ROW) ? 1 : N;
+    const bool in_stream = (p.flags & F_IN_STREAM) != 0;
+    const bool out_stream = (p.flags & F_OUT_STREAM) != 0;
+    const bool state_stream = (p.flags & F_STATE_STREAM) != 0;
+    const bool inv = (p.flags & F_INVERSE) != 0;
 
-    cx<T> v[E];
-#pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int pos = t + TPL * m;
-        v[m] = active ? p.in[base + pos * STRIDE] : mk<T>(0, 0);
-    }
-
-    if (p.mask_kind != MASK_NONE && active) {
-        if (p.mask_kind == MASK_CX) {
-            const cx<T>* mk_ = static_cast<const cx<T>*>(p.mask);
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], mk_[mbase + (t + TPL * m) * STRIDE]);
-        } else if (p.mask_kind == MASK_REAL) {
-            const T* mk_ = static_cast<const T*>(p.mask);
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const T f = mk_[mbase + (t + TPL * m) * STRIDE];
-                v[m].x *= f; v[m].y *= f;
-            }
-        } else {
-            const unsigned char* mk_ = static_cast<const unsigned char*>(p.mask);
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const T f = mk_[mbase + (t + TPL * m) * STRIDE] ? (T)1 : (T)0;
-                v[m].x *= f; v[m].y *= f;
-            }
-        }
-    }
-
-    if (PRE == PRE_LENS) {
-        const double f2 = __ldg(&p.x2_tab[fixed]);
-#pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const double g2 = __ldg(&p.x2_tab[t + TPL * m]);
-            // (X^2 + Y^2): X indexes columns, Y rows; the sum is commutative so the order is immaterial
-            v[m] = cmul(v[m], lens_factor<T>(AXIS == AX_ROW ? g2 : f2, AXIS == AX_ROW ? f2 : g2, p.lens_k0, p.lens_2f));
-        }
-    }
-    if (PRE == PRE_H) {
-        // rows: fixed = j -> b[j]; columns: fixed = i -> a[i]
+    cx<T>* sH = nullptr;
+    if constexpr (PRE == PRE_H) {
+        // H for this thread's samples, kept at [line][pos]: written and read by the same thread
+        sH = reinterpret_cast<cx<T>*>(smem_raw + K::SMEM_X) + l * N;
         const double fx = (AXIS == AX_ROW) ? __ldg(&p.b_tab[fixed]) : __ldg(&p.a_tab[fixed]);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int pos = t + TPL * m;
             const double a_i = (AXIS == AX_ROW) ? __ldg(&p.a_tab[pos]) : fx;
             const double b_j = (AXIS == AX_ROW) ? fx : __ldg(&p.b_tab[pos]);
-            v[m] = cmul(v[m], transfer_factor<T>(a_i, b_j, p.z));
+            sH[pos] = transfer_factor<T>(a_i, b_j, p.z);
         }
     }
-    if (p.out_pre != nullptr && active) {
-#pragma unroll
-        for (int m = 0; m < E; ++m) p.out_pre[base + (t + TPL * m) * STRIDE] = v[m];
-    }
 
-    if (MID == MID_H) {
-        // column pass of the fresh chain: FFT_y, transfer function, inverse FFT_y
-        line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
-        const double a_i = __ldg(&p.a_tab[fixed]);            // AXIS == AX_COL
+    for (int g = 0; g < p.groups; ++g) {
+        const bool active = in_range && (beam + (long long)g * p.group_beams < p.nbeams);
+        const long long gb = base + (long long)g * p.group_beams * p.beam_stride;
+
+        cx<T> v[E];
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const cx<T> h = transfer_factor<T>(a_i, __ldg(&p.b_tab[t + TPL * m]), p.z);
-            v[m] = cmul(v[m], h);
+            const int pos = t + TPL * m;
+            v[m] = active ? ld_cx(&p.in[gb + pos * STRIDE], in_stream) : mk<T>(0, 0);
         }
-        if (p.out_mid != nullptr && active) {
-#pragma unroll
-            for (int m = 0; m < E; ++m) p.out_mid[base + (t + TPL * m) * STRIDE] = v[m];
-        }
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
-        line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
-    } else {
-        const bool inv = (p.flags & F_INVERSE) != 0;
-        if (inv) {
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
-        }
-        line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
-        if (inv) {
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
-        }
-    }
 
-    if (!active) return;
-    const T sc = p.scale;
+        if (p.mask_kind != MASK_NONE && active) {
+            const long long gm = mbase + (long long)g * p.group_beams * p.mask_beam_stride;
+            if (p.mask_kind == MASK_CX) {
+                const cx<T>* mk_ = static_cast<const cx<T>*>(p.mask);
 #pragma unroll
-    for (int m = 0; m < E; ++m) { v[m].x *= sc; v[m].y *= sc; }
-    if (p.out != nullptr) {
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], mk_[gm + (t + TPL * m) * STRIDE]);
+            } else if (p.mask_kind == MASK_REAL) {
+                const T* mk_ = static_cast<const T*>(p.mask);
 #pragma unroll
-        for (int m = 0; m < E; ++m) p.out[base + (t + TPL * m) * STRIDE] = v[m];
-    }
-    if (p.inten != nullptr) {
+                for (int m = 0; m < E; ++m) {
+                    const T f = mk_[gm + (t + TPL * m) * STRIDE];
+                    v[m].x *= f; v[m].y *= f;
+                }
+            } else {
+                const unsigned char* mk_ = static_cast<const unsigned char*>(p.mask);
 #pragma unroll
-        for (int m = 0; m < E; ++m) p.inten[base + (t + TPL * m) * STRIDE] = v[m].x * v[m].x + v[m].y * v[m].y;
+                for (int m = 0; m < E; ++m) {
+                    const T f = mk_[gm + (t + TPL * m) * STRIDE] ? (T)1 : (T)0;
+                    v[m].x *= f; v[m].y *= f;
+                }
+            }
+        }
+
+        if constexpr (PRE == PRE_LENS) {
+            const double f2 = __ldg(&p.x2_tab[fixed]);
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const double g2 = __ldg(&p.x2_tab[t + TPL * m]);
+                // (X^2 + Y^2): X indexes columns, Y rows; the sum is commutative
+                v[m] = cmul(v[m], lens_factor<T>(AXIS == AX_ROW ? g2 : f2, AXIS == AX_ROW ? f2 : g2, p.lens_k0, p.lens_2f));
+            }
+        }
+        if constexpr (PRE == PRE_H) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], sH[t + TPL * m]);
+        }
+        if (p.out_pre != nullptr && active) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) st_cx(&p.out_pre[gb + (t + TPL * m) * STRIDE], v[m], state_stream);
+        }
+
+        if constexpr (MID == MID_H) {
+            // column pass of the fresh chain: FFT_y, transfer function, inverse FFT_y
+            line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
+            const double a_i = __ldg(&p.a_tab[fixed]);            // AXIS == AX_COL
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const cx<T> h = transfer_factor<T>(a_i, __ldg(&p.b_tab[t + TPL * m]), p.z);
+                v[m] = cmul(v[m], h);
+            }
+            if (p.out_mid != nullptr && active) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) st_cx(&p.out_mid[gb + (t + TPL * m) * STRIDE], v[m], state_stream);
+            }
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+            line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+        } else {
+            if (inv) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+            }
+            line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
+            if (inv) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+            }
+        }
+
+        if (active) {
+            const T sc = p.scale;
+            if (sc != (T)1) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) { v[m].x *= sc; v[m].y *= sc; }
+            }
+            if (p.out != nullptr) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) st_cx(&p.out[gb + (t + TPL * m) * STRIDE], v[m], out_stream);
+            }
+            if (p.inten != nullptr) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) __stcs(&p.inten[gb + (t + TPL * m) * STRIDE], v[m].x * v[m].x + v[m].y * v[m].y);
+            }
+        }
     }
 }
 

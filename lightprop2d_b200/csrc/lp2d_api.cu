@@ -45,6 +45,12 @@ struct lp2d_plan {
     void* tw;          // device twiddles (cx<T>)
     double* tabs;      // device: a | b | x2, n doubles each
     long long chunk_bytes;   // intermediate kept per kernel pair (L2 residency)
+    int h_groups;            // beam slabs one CTA of the H row pass walks over
+    int hints;               // use evict-first accesses for streaming data
+    int nstreams;            // auxiliary streams the chunks are fanned out over
+    cudaStream_t aux[8];
+    cudaEvent_t ev_fork;
+    cudaEvent_t ev_join[8];
 };
 
 #define LP2D_CHECK_PLAN(p)                                                      \
@@ -89,8 +95,10 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     if (dtype != LP2D_C64 && dtype != LP2D_C128) return fail(LP2D_EINVAL, "plan_create: dtype must be LP2D_C64 or LP2D_C128");
     if (host_a == nullptr || host_b == nullptr || host_x2 == nullptr)
         return fail(LP2D_EINVAL, "plan_create: grid tables must not be NULL");
-    const SizeOps<float>* o32 = dtype == LP2D_C64 ? find_ops_f32(n) : nullptr;
-    const SizeOps<double>* o64 = dtype == LP2D_C128 ? find_ops_f64(n) : nullptr;
+    const char* venv = getenv("LP2D_VARIANT");
+    const int variant = venv ? atoi(venv) : 0;
+    const SizeOps<float>* o32 = dtype == LP2D_C64 ? find_ops_f32(n, variant) : nullptr;
+    const SizeOps<double>* o64 = dtype == LP2D_C128 ? find_ops_f64(n, variant) : nullptr;
     if (o32 == nullptr && o64 == nullptr) {
         char buf[160];
         snprintf(buf, sizeof buf, "plan_create: npoints=%d not supported for %s (powers of two %d..%d)", n,
@@ -108,6 +116,24 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     const char* env = getenv("LP2D_CHUNK_MB");
     p->chunk_bytes = (env ? atoll(env) : 32) * (1ll << 20);
     if (p->chunk_bytes <= 0) p->chunk_bytes = 1ll << 62;
+    env = getenv("LP2D_HGROUPS");
+    p->h_groups = env ? atoi(env) : 8;
+    env = getenv("LP2D_HINTS");
+    p->hints = env ? atoi(env) : 1;
+    env = getenv("LP2D_STREAMS");
+    p->nstreams = env ? atoi(env) : 4;
+    if (p->nstreams < 1) p->nstreams = 1;
+    if (p->nstreams > 8) p->nstreams = 8;
+    if (p->nstreams > 1) {
+        for (int i = 0; i < p->nstreams; ++i) {
+            if ((e = cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) {
+                delete p;
+                return cuda_fail(e, "aux stream/event create");
+            }
+        }
+        if ((e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming)) != cudaSuccess) { delete p; return cuda_fail(e, "event create"); }
+    }
 
     std::vector<double> w;
     if (o32) o32->twiddles(w); else o64->twiddles(w);
@@ -139,6 +165,10 @@ int lp2d_plan_destroy(lp2d_plan* p) {
     if (p == nullptr) return LP2D_OK;
     cudaFree(p->tw);
     cudaFree(p->tabs);
+    if (p->nstreams > 1) {
+        for (int i = 0; i < p->nstreams; ++i) { cudaStreamDestroy(p->aux[i]); cudaEventDestroy(p->ev_join[i]); }
+        cudaEventDestroy(p->ev_fork);
+    }
     delete p;
     return LP2D_OK;
 }
@@ -162,6 +192,7 @@ LineArgs<T> base_args(const lp2d_plan* p) {
     a.x2_tab = p->tabs + 2 * p->n;
     a.scale = (T)1;
     a.beam_stride = (long long)p->n * p->n;
+    a.groups = 1;
     return a;
 }
 
@@ -183,14 +214,51 @@ long long chunk_beams(const lp2d_plan* p, long long batch) {
         if (e__ != cudaSuccess) return cuda_fail(e__, what);        \
     } while (0)
 
+// Chunks of a batch are independent: fan them out over the plan's auxiliary streams so the
+// tail of one chunk's kernel overlaps the head of the next, then join back on the user stream.
+struct Fan {
+    const lp2d_plan* p;
+    cudaStream_t user;
+    int ns, k;
+    Fan(const lp2d_plan* plan, cudaStream_t u, long long nchunks) : p(plan), user(u), ns(0), k(0) {
+        if (nchunks > 1 && plan->nstreams > 1) ns = (int)(nchunks < plan->nstreams ? nchunks : plan->nstreams);
+    }
+    cudaError_t fork() {
+        if (!ns) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(p->ev_fork, user);
+        for (int i = 0; i < ns && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(p->aux[i], p->ev_fork, 0);
+        return e;
+    }
+    cudaStream_t next() { return ns ? p->aux[k++ % ns] : user; }
+    cudaError_t join() {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < ns && e == cudaSuccess; ++i) {
+            e = cudaEventRecord(p->ev_join[i], p->aux[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, p->ev_join[i], 0);
+        }
+        return e;
+    }
+};
+
 template <typename T>
 int rows(const lp2d_plan* p, int pre, LineArgs<T> a, long long beams, cudaStream_t s) {
-    a.nlines = (int)(beams * p->n);
+    // the transfer function is the same for every beam: let a CTA reuse it over `groups` slabs
+    long long groups = (pre == PRE_H) ? p->h_groups : 1;
+    if (groups > beams) groups = beams;
+    if (groups < 1) groups = 1;
+    const long long gbeams = (beams + groups - 1) / groups;
+    a.groups = (int)((beams + gbeams - 1) / gbeams);
+    a.group_beams = gbeams;
+    a.nbeams = beams;
+    a.nlines = (int)(gbeams * p->n);
     LP2D_CU(ops_of<T>(p)->row(pre, a, s), "row pass launch");
     return LP2D_OK;
 }
 template <typename T>
 int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream_t s) {
+    a.groups = 1;
+    a.group_beams = beams;
+    a.nbeams = beams;
     a.nlines = (int)(beams * (p->n / ops_of<T>(p)->w_col));
     LP2D_CU(ops_of<T>(p)->col(mid, a, s), "column pass launch");
     return LP2D_OK;
@@ -203,13 +271,17 @@ int mul_fft2(const lp2d_plan* p, const void* in, void* state_out, void* other, c
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
     const T sc = inverse ? (T)(1.0 / (double)p->n) : (T)1;
+    const int H = p->hints;
+    Fan fan(p, s, (batch + cb - 1) / cb);
+    LP2D_CU(fan.fork(), "stream fork");
     for (long long b0 = 0; b0 < batch; b0 += cb) {
         const long long nb = (batch - b0 < cb) ? batch - b0 : cb;
+        s = fan.next();
         LineArgs<T> a = base_args<T>(p);
         a.in = static_cast<const cx<T>*>(in) + b0 * plane;
         a.out = static_cast<cx<T>*>(other) + b0 * plane;
         a.out_pre = state_out ? static_cast<cx<T>*>(state_out) + b0 * plane : nullptr;
-        a.flags = inverse ? F_INVERSE : 0;
+        a.flags = (inverse ? F_INVERSE : 0) | (H ? (F_IN_STREAM | F_STATE_STREAM) : 0);
         a.scale = sc;
         a.lens_k0 = k0; a.lens_2f = two_f;
         if (mask != nullptr) {
@@ -222,10 +294,11 @@ int mul_fft2(const lp2d_plan* p, const void* in, void* state_out, void* other, c
         if (rc) return rc;
         LineArgs<T> c = base_args<T>(p);
         c.in = a.out; c.out = a.out;
-        c.flags = a.flags; c.scale = sc;
+        c.flags = (inverse ? F_INVERSE : 0) | (H ? F_OUT_STREAM : 0); c.scale = sc;
         rc = cols<T>(p, MID_NONE, c, nb, s);
         if (rc) return rc;
     }
+    LP2D_CU(fan.join(), "stream join");
     return LP2D_OK;
 }
 
@@ -235,24 +308,29 @@ int propagate_state(const lp2d_plan* p, void* spectrum, void* field, void* inten
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
     const T sc = (T)(1.0 / (double)p->n);
+    const int H = p->hints;
+    Fan fan(p, s, (batch + cb - 1) / cb);
+    LP2D_CU(fan.fork(), "stream fork");
     for (long long b0 = 0; b0 < batch; b0 += cb) {
         const long long nb = (batch - b0 < cb) ? batch - b0 : cb;
+        s = fan.next();
         // rows: spectrum *= H (stored back), inverse row transform -> field buffer
         LineArgs<T> a = base_args<T>(p);
         a.in = static_cast<const cx<T>*>(spectrum) + b0 * plane;
         a.out_pre = static_cast<cx<T>*>(spectrum) + b0 * plane;
         a.out = static_cast<cx<T>*>(field) + b0 * plane;
-        a.flags = F_INVERSE; a.scale = sc; a.z = z;
+        a.flags = F_INVERSE | (H ? (F_IN_STREAM | F_STATE_STREAM) : 0); a.scale = sc; a.z = z;
         int rc = rows<T>(p, PRE_H, a, nb, s);
         if (rc) return rc;
         // columns: inverse transform in place, optional |E|^2
         LineArgs<T> c = base_args<T>(p);
         c.in = a.out; c.out = a.out;
         c.inten = intensity ? static_cast<T*>(intensity) + b0 * plane : nullptr;
-        c.flags = F_INVERSE; c.scale = sc;
+        c.flags = F_INVERSE | (H ? F_OUT_STREAM : 0); c.scale = sc;
         rc = cols<T>(p, MID_NONE, c, nb, s);
         if (rc) return rc;
     }
+    LP2D_CU(fan.join(), "stream join");
     return LP2D_OK;
 }
 
@@ -268,18 +346,25 @@ int propagate_fresh(const lp2d_plan* p, const void* fin, void* fout, void* spec_
         if (cb > fit) cb = fit;
     }
     const T sc = (T)(1.0 / (double)p->n);
+    const int H = p->hints;
+    // the shared work buffer serialises the chunks; with per-chunk output buffers they fan out
+    Fan fan(p, s, via_work ? 1 : (batch + cb - 1) / cb);
+    LP2D_CU(fan.fork(), "stream fork");
     for (long long b0 = 0; b0 < batch; b0 += cb) {
         const long long nb = (batch - b0 < cb) ? batch - b0 : cb;
+        s = fan.next();
         cx<T>* buf = via_work ? static_cast<cx<T>*>(work) : static_cast<cx<T>*>(fout) + b0 * plane;
         // 1. forward row transform: field -> buf
         LineArgs<T> a = base_args<T>(p);
         a.in = static_cast<const cx<T>*>(fin) + b0 * plane;
         a.out = buf;
+        a.flags = H ? F_IN_STREAM : 0;
         int rc = rows<T>(p, PRE_NONE, a, nb, s);
         if (rc) return rc;
         // 2. fused column pass in place: FFT_y, H, inverse FFT_y (scaled 1/N)
         LineArgs<T> c = base_args<T>(p);
         c.in = buf; c.out = buf; c.z = z; c.scale = sc;
+        c.flags = H ? F_STATE_STREAM : 0;
         c.out_mid = spec_out ? static_cast<cx<T>*>(spec_out) + b0 * plane : nullptr;
         rc = cols<T>(p, MID_H, c, nb, s);
         if (rc) return rc;
@@ -287,11 +372,12 @@ int propagate_fresh(const lp2d_plan* p, const void* fin, void* fout, void* spec_
         LineArgs<T> r = base_args<T>(p);
         r.in = buf;
         r.out = via_work ? nullptr : buf;
-        r.flags = F_INVERSE; r.scale = sc;
+        r.flags = F_INVERSE | (H ? F_OUT_STREAM : 0); r.scale = sc;
         r.inten = intensity ? static_cast<T*>(intensity) + b0 * plane : nullptr;
         rc = rows<T>(p, PRE_NONE, r, nb, s);
         if (rc) return rc;
     }
+    LP2D_CU(fan.join(), "stream join");
     return LP2D_OK;
 }
 

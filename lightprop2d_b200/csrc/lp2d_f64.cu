@@ -13,8 +13,13 @@ static const SizeOps<double> kOpsF64[] = {
     Ops<double, 2048, 8, 1, 2>::entry(),
     Ops<double, 4096, 8, 1, 1>::entry(),
 };
-const SizeOps<double>* find_ops_f64(int n) {
-    for (const auto& o : kOpsF64) if (o.n == n) return &o;
-    return nullptr;
+const SizeOps<double>* find_ops_f64(int n, int variant) {
+    const SizeOps<double>* first = nullptr;
+    for (const auto& o : kOpsF64) {
+        if (o.n != n) continue;
+        if (o.variant == variant) return &o;
+        if (first == nullptr) first = &o;
+    }
+    return first;
 }
 }  // namespace lp2d

@@ -8,11 +8,11 @@ namespace lp2d {
 template <typename T, int N, int E, int WR, int WC>
 struct Ops {
     using LP = LinePlan<N, E>;
-    using KR = KCfg<T, N, E, AX_ROW, WR>;
     using KC = KCfg<T, N, E, AX_COL, WC>;
 
     template <int PRE>
     static cudaError_t launch_row(const LineArgs<T>& a, cudaStream_t s) {
+        using KR = KCfg<T, N, E, AX_ROW, WR, PRE>;
         const unsigned grid = (unsigned)((a.nlines + WR - 1) / WR);
         line_kernel<T, N, E, AX_ROW, WR, PRE, MID_NONE><<<grid, KR::THREADS, KR::SMEM, s>>>(a);
         ++g_launches;
@@ -46,9 +46,9 @@ struct Ops {
     }
     static cudaError_t configure() {
         cudaError_t e;
-        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_NONE, MID_NONE>, KR::SMEM)) != cudaSuccess) return e;
-        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_LENS, MID_NONE>, KR::SMEM)) != cudaSuccess) return e;
-        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_H, MID_NONE>, KR::SMEM)) != cudaSuccess) return e;
+        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_NONE, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_NONE>::SMEM)) != cudaSuccess) return e;
+        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_LENS, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_LENS>::SMEM)) != cudaSuccess) return e;
+        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_H, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_H>::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_NONE>, KC::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_H>, KC::SMEM)) != cudaSuccess) return e;
         return cudaSuccess;
@@ -67,8 +67,8 @@ struct Ops {
                 }
         }
     }
-    static constexpr SizeOps<T> entry() {
-        return SizeOps<T>{N, E, LP::tw_size(), WR, WC, &row, &col, &configure, &twiddles};
+    static constexpr SizeOps<T> entry(int variant = 0) {
+        return SizeOps<T>{N, E, LP::tw_size(), WR, WC, variant, &row, &col, &configure, &twiddles};
     }
 };
 
