@@ -74,7 +74,7 @@ def _get_plan(device_index, n, bits, area_size, wl, a_tab, b_tab, x2_tab):
     key = (device_index, n, bits, float(area_size), float(wl), x2_tab.tobytes())
     p = _PLAN_CACHE.get(key)
     if p is None:
-        if len(_PLAN_CACHE) > 64:
+        if len(_PLAN_CACHE) > 16:
             _PLAN_CACHE.clear()
         torch = _torch()
         with torch.cuda.device(device_index):

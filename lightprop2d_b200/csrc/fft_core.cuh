@@ -37,6 +37,42 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }
 template <typename C> __device__ __forceinline__ C cswap(C a) { C r; r.x = a.y; r.y = a.x; return r; }
+template <typename C> __device__ __forceinline__ C cconj(C a) { C r; r.x = a.x; r.y = -a.y; return r; }
+
+// complex64 arithmetic in the packed f32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2):
+// a complex sample is one 64-bit register pair, a complex add is ONE instruction, a complex
+// multiply is two.  The half swap, the per-half negation and the scalar broadcast written
+// below with make_float2 are operand modifiers of those instructions (R.F32x2.LO_HI, .NP,
+// R.F32), not extra moves.  Enabled per translation unit with LP2D_PACKED_F32 (the pipeline
+// kernels, which are issue bound); the one-kernel-per-pass line kernels are latency bound and
+// measured ~5 % slower with the pair-aligned register allocation, so they keep scalar FP32.
+#if defined(LP2D_PACKED_F32) && defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b) { return __fadd2_rn(a, b); }
+template <> __device__ __forceinline__ float2 csub<float2>(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+template <> __device__ __forceinline__ float2 cmul<float2>(float2 a, float2 b) {
+    // (ax bx - ay by, ax by + ay bx) = bx * (ax, ay) + by * (-ay, ax): the halves of b enter as
+    // broadcast scalars, the swap + half negation of a is an operand modifier of FFMA2
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
+#endif
+// a * s for a real s
+__device__ __forceinline__ float2 cscale(float2 a, float s) {
+#if defined(LP2D_PACKED_F32) && defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __fmul2_rn(a, make_float2(s, s));
+#else
+    return make_float2(a.x * s, a.y * s);
+#endif
+}
+__device__ __forceinline__ double2 cscale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+// (a.x * s.x, a.y * s.y)
+__device__ __forceinline__ float2 cmul_each(float2 a, float2 s) {
+#if defined(LP2D_PACKED_F32) && defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __fmul2_rn(a, s);
+#else
+    return make_float2(a.x * s.x, a.y * s.y);
+#endif
+}
+__device__ __forceinline__ double2 cmul_each(double2 a, double2 s) { return make_double2(a.x * s.x, a.y * s.y); }
 
 // cos(2*pi*k/32), k = 0..8
 __host__ __device__ constexpr double kCos32(int k) {
@@ -56,18 +92,18 @@ template <typename T>
 __device__ __forceinline__ cx<T> mul_w32(cx<T> d, int k32) {
     if (k32 == 0) return d;
     if (k32 == 8) return mk<T>(d.y, -d.x);                       // * (-i)
-    if (k32 == 4) {                                              // * (1-i)/sqrt2
+    if (k32 == 4) {                                              // * (1-i)/sqrt2 : (d + (-i) d) h
         const T h = (T)kCos32(4);
-        return mk<T>((d.x + d.y) * h, (d.y - d.x) * h);
+        return cscale(cadd(d, mk<T>(d.y, -d.x)), h);
     }
-    if (k32 == 12) {                                             // * (-1-i)/sqrt2
+    if (k32 == 12) {                                             // * (-1-i)/sqrt2 : ((-i) d - d) h
         const T h = (T)kCos32(4);
-        return mk<T>((d.y - d.x) * h, -(d.x + d.y) * h);
+        return cscale(csub(mk<T>(d.y, -d.x), d), h);
     }
-    // general: w = c - i s  with c = cos(2 pi k/32), s = sin(2 pi k/32)
+    // general: w = c - i s  with c = cos(2 pi k/32), s = sin(2 pi k/32):  d w = c d + s ((-i) d)
     const T c = (T)(k32 <= 8 ? kCos32(k32) : -kCos32(16 - k32));
     const T s = (T)(k32 <= 8 ? kCos32(8 - k32) : kCos32(k32 - 8));
-    return mk<T>(d.x * c + d.y * s, d.y * c - d.x * s);
+    return cmul(mk<T>(c, -s), d);
 }
 
 __host__ __device__ constexpr int ilog2(int v) { int l = 0; while (v > 1) { v >>= 1; ++l; } return l; }
@@ -190,8 +226,18 @@ __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sli
             for (int r = 0; r < R; ++r) v[q + r * Q] = u[r];
         } else {
             const int base = (j / Ns) * (Ns * R) + (j & (Ns - 1));
+            // pad(base + r*Ns) is affine in r when a step of Ns never carries into the padding
+            // differently: Ns a multiple of PADSTEP, or the whole butterfly inside one PADSTEP block
+            constexpr bool affine = (Ns % LP::PADSTEP == 0) || (LP::PADSTEP % (Ns * R) == 0);
+            if constexpr (affine) {
+                constexpr int RS = (Ns % LP::PADSTEP == 0) ? Ns + Ns / LP::PADSTEP : Ns;
+                cx<T>* d = sline + LP::pad(base);
 #pragma unroll
-            for (int r = 0; r < R; ++r) sline[LP::pad(base + r * Ns)] = u[r];
+                for (int r = 0; r < R; ++r) d[r * RS] = u[r];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) sline[LP::pad(base + r * Ns)] = u[r];
+            }
         }
     }
 }
