@@ -9,6 +9,7 @@
 #include "../../include/lp2d.h"
 #include "dispatch.h"
 #include "pipe_ops.cuh"
+#include "pipe2_ops.cuh"
 
 namespace lp2d {
 long long g_launches = 0;
@@ -63,6 +64,16 @@ struct lp2d_plan {
     int counters_cap;
     int pipe_g, pipe_lag, pipe_slots, pipe_grid;   // tuning overrides (0 = automatic)
     int pipe_mode;             // 0: persistent CTAs, 1: one CTA per item (ticket)
+    int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
+    int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
+    // fused step kernel (pipe2.cuh)
+    const P2Ops<float>* p2_32;
+    const P2Ops<double>* p2_64;
+    int p2_ctas_factor, p2_ctas_plain;
+    void* p2_tw;               // twiddles of the P2 (N, E) schedule
+    void* p2_fac;              // factor plane [n][fl]
+    int fac_kind, fac_by_column;   // what p2_fac currently holds (0 = nothing)
+    double fac_p0, fac_p1;
 };
 
 #define LP2D_CHECK_PLAN(p)                                                      \
@@ -206,10 +217,58 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             p->pipe32 = q32; p->pipe64 = q64; p->ring_bytes = ring_bytes;
         }
     }
+    p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0;
+    env = getenv("LP2D_PIPE");
+    if (env != nullptr && atoi(env) == 2) {
+        env = getenv("LP2D_PIPE_VARIANT");
+        const int pvar = env ? atoi(env) : 0;
+        const P2Ops<float>* q32 = dtype == LP2D_C64 ? find_p2_f32(n, pvar) : nullptr;
+        const P2Ops<double>* q64 = dtype == LP2D_C128 ? find_p2_f64(n, pvar) : nullptr;
+        if (q32 || q64) {
+            env = getenv("LP2D_RING_MB");
+            const long long ring_bytes = (env ? atoll(env) : 64) * (1ll << 20);
+            const size_t csz = dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2);
+            std::vector<double> w2;
+            if (q32) q32->twiddles(w2); else q64->twiddles(w2);
+            const size_t n2 = w2.size() / 2;
+            e = q32 ? q32->configure(&p->p2_ctas_factor, &p->p2_ctas_plain) : q64->configure(&p->p2_ctas_factor, &p->p2_ctas_plain);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
+            p->counters_cap = 1 + PIPE_MAX_STAGES * 16384;
+            if (e == cudaSuccess) e = cudaMalloc(&p->ring, (size_t)ring_bytes);
+            if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * p->counters_cap);
+            if (e == cudaSuccess) e = cudaMalloc(&p->p2_tw, n2 * csz);
+            if (e == cudaSuccess) e = cudaMalloc(&p->p2_fac, (size_t)n * (q32 ? q32->fl : q64->fl) * csz);
+            if (e == cudaSuccess) {
+                if (dtype == LP2D_C64) {
+                    std::vector<float> wf(w2.size());
+                    for (size_t i = 0; i < w2.size(); ++i) wf[i] = (float)w2[i];
+                    e = cudaMemcpy(p->p2_tw, wf.data(), n2 * csz, cudaMemcpyHostToDevice);
+                } else {
+                    e = cudaMemcpy(p->p2_tw, w2.data(), n2 * csz, cudaMemcpyHostToDevice);
+                }
+            }
+            if (e != cudaSuccess || p->p2_ctas_factor < 1 || p->p2_ctas_plain < 1) {
+                cudaFree(p->ring); cudaFree(p->counters); cudaFree(p->p2_tw); cudaFree(p->p2_fac); cudaFree(p->tw); cudaFree(p->tabs); delete p;
+                return e != cudaSuccess ? cuda_fail(e, "fused step kernel setup") : fail(LP2D_ECUDA, "fused step kernel does not fit an SM");
+            }
+            p->p2_32 = q32; p->p2_64 = q64; p->ring_bytes = ring_bytes;
+        }
+    }
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_LAG");   p->pipe_lag = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_SLOTS"); p->pipe_slots = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_GRID");  p->pipe_grid = env ? atoi(env) : 0;
+    env = getenv("LP2D_PIPE_HINTS"); p->pipe_hints = env ? atoi(env) : 3;
+    env = getenv("LP2D_PIPE_PERSIST"); p->pipe_persist = env ? atoi(env) : 0;
+    if (p->pipe_persist && p->ring != nullptr) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+            size_t want = (size_t)p->ring_bytes;
+            if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); p->pipe_persist = 0; }
+            if (getenv("LP2D_VERBOSE")) fprintf(stderr, "[lp2d] L2 %d MB, persisting max %d MB, set %zu MB\n", prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, want >> 20);
+        }
+    }
     *out = p;
     return LP2D_OK;
 }
@@ -220,6 +279,8 @@ int lp2d_plan_destroy(lp2d_plan* p) {
     cudaFree(p->tabs);
     cudaFree(p->ring);
     cudaFree(p->counters);
+    cudaFree(p->p2_tw);
+    cudaFree(p->p2_fac);
     if (p->nstreams > 1) {
         for (int i = 0; i < p->nstreams; ++i) { cudaStreamDestroy(p->aux[i]); cudaEventDestroy(p->ev_join[i]); }
         cudaEventDestroy(p->ev_fork);
@@ -250,6 +311,105 @@ template <> const PipeOps<double>* pipe_of<double>(const lp2d_plan* p) { return 
 template <typename T>
 StageArgs<T> stage(int axis, int inverse, T scale) {
     StageArgs<T> st;
+    memset(&st, 0, sizeof st);
+    st.axis = axis; st.inverse = inverse; st.scale = scale;
+    return st;
+}
+
+
+template <typename T> const P2Ops<T>* p2_of(const lp2d_plan* p);
+template <> const P2Ops<float>* p2_of<float>(const lp2d_plan* p) { return p->p2_32; }
+template <> const P2Ops<double>* p2_of<double>(const lp2d_plan* p) { return p->p2_64; }
+
+// Make the plan's factor plane hold (kind, layout, parameters); it is rebuilt only when they change
+// (a z-sweep with a constant step reuses it for every call).
+template <typename T>
+int p2_ensure_factor(lp2d_plan* p, int kind, int by_column, double p0, double p1, cudaStream_t s) {
+    if (p->fac_kind == kind && p->fac_by_column == by_column && p->fac_p0 == p0 && p->fac_p1 == p1) return LP2D_OK;
+    const P2Ops<T>* ops = p2_of<T>(p);
+    cudaError_t e;
+    if (sizeof(T) == 4)
+        e = p2_factor_plane_f32(static_cast<float2*>(p->p2_fac), p->tabs, p->n, ops->fl, kind, by_column,
+                                kind == P2_FAC_H ? p0 : 0.0, kind == P2_FAC_LENS ? p0 : 0.0, kind == P2_FAC_LENS ? p1 : 0.0, s);
+    else
+        e = p2_factor_plane_f64(static_cast<double2*>(p->p2_fac), p->tabs, p->n, ops->fl, kind, by_column,
+                                kind == P2_FAC_H ? p0 : 0.0, kind == P2_FAC_LENS ? p0 : 0.0, kind == P2_FAC_LENS ? p1 : 0.0, s);
+    if (e != cudaSuccess) return cuda_fail(e, "factor plane launch");
+    p->fac_kind = kind; p->fac_by_column = by_column; p->fac_p0 = p0; p->fac_p1 = p1;
+    return LP2D_OK;
+}
+
+// Run a chain of `nstages` line passes over `batch` beams in one launch of the fused step kernel.
+// fac_kind: P2_FAC_NONE / P2_FAC_H (p0 = z) / P2_FAC_LENS (p0 = k0, p1 = 2f); by_column: layout of the
+// factor plane (1 for the fused column stage).  Returns -1 when the kernel is not available.
+template <typename T>
+int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, int by_column, double p0, double p1,
+           long long batch, cudaStream_t s) {
+    const P2Ops<T>* ops = p2_of<T>(p);
+    if (ops == nullptr) return -1;
+    const bool need_factor = fac_kind != P2_FAC_NONE;
+    const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
+    const int ctas = need_factor ? p->p2_ctas_factor : p->p2_ctas_plain;
+    long long conc = (long long)ctas * p->num_sms;
+    if (p->pipe_grid > 0 && p->pipe_grid < conc) conc = p->pipe_grid;
+    const int tiles = ops->tiles;
+    long long G = p->pipe_g > 0 ? p->pipe_g : 1;
+    if (G > batch) G = batch;
+    // lag (in groups) between consecutive stages of a group: the items in between cover every resident
+    // CTA twice (an item's dependencies are looked at one item ahead of its start)
+    const long long reach = 2 * conc;
+    int lag = p->pipe_lag > 0 ? p->pipe_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles));
+    if (lag < 1) lag = 1;
+    // ring slots (groups): the stage that refills a slot must also be `lag` groups behind the last
+    // stage of the group that held it
+    int slots = nstages * lag;
+    if (p->pipe_slots > 0) slots = p->pipe_slots > (nstages - 1) * lag + 1 ? p->pipe_slots : (nstages - 1) * lag + 1;
+    while (G > 1 && slots * G * plane > p->ring_bytes) --G;
+    if (slots * G * plane > p->ring_bytes) return -1;
+    if (need_factor) {
+        const int rc = p2_ensure_factor<T>(p, fac_kind, by_column, p0, p1, s);
+        if (rc) return rc;
+    }
+    const long long groups_cap = (p->counters_cap - 1) / nstages;
+    for (long long b0 = 0; b0 < batch; b0 += groups_cap * G) {
+        const long long nb = (batch - b0 < groups_cap * G) ? batch - b0 : groups_cap * G;
+        P2Args<T> a;
+        memset(&a, 0, sizeof a);
+        const long long off = b0 * (long long)p->n * p->n;
+        for (int i = 0; i < nstages; ++i) {
+            a.st[i] = stages[i];
+            P2Stage<T>& st = a.st[i];
+            if (st.in) st.in += off;
+            if (st.out) st.out += off;
+            if (st.out_pre) st.out_pre += off;
+            if (st.out_mid) st.out_mid += off;
+            if (st.inten) st.inten += off;
+            if (st.mask) st.mask = static_cast<const char*>(st.mask) + b0 * st.mask_beam_stride *
+                                   (st.mask_kind == MASK_CX ? sizeof(cx<T>) : st.mask_kind == MASK_REAL ? sizeof(T) : 1);
+        }
+        a.ring = static_cast<cx<T>*>(p->ring);
+        a.tw = static_cast<const cx<T>*>(p->p2_tw);
+        a.fac = static_cast<const cx<T>*>(p->p2_fac);
+        a.counters = p->counters;
+        a.nbeams = nb;
+        a.nstages = nstages;
+        a.ngroups = (int)((nb + G - 1) / G);
+        a.G = (int)G; a.lag = lag; a.ring_slots = slots;
+        a.fac_map = fac_kind == P2_FAC_LENS ? P2_MAP_CENTRE : P2_MAP_FREQ;
+        a.hints = p->pipe_hints;
+        const long long total = ((long long)a.ngroups + (long long)(nstages - 1) * lag) * nstages * tiles;
+        if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "fused step: batch too large for one launch");
+        a.total_items = (int)total;
+        LP2D_CU(cudaMemsetAsync(p->counters, 0, sizeof(unsigned int) * (1 + (size_t)nstages * a.ngroups), s), "fused step counters");
+        const unsigned grid = (unsigned)(total < conc ? total : conc);
+        LP2D_CU(ops->launch(a, grid, need_factor, s, p->ring, p->pipe_persist ? (size_t)(slots * G * plane) : 0), "fused step launch");
+    }
+    return LP2D_OK;
+}
+
+template <typename T>
+P2Stage<T> p2_stage(int axis, int inverse, T scale) {
+    P2Stage<T> st;
     memset(&st, 0, sizeof st);
     st.axis = axis; st.inverse = inverse; st.scale = scale;
     return st;
@@ -405,9 +565,21 @@ int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream
 
 // data *= mask (optional), state stored to `data`, other = (i)fft2(data)
 template <typename T>
-int mul_fft2(const lp2d_plan* p, const void* in, void* state_out, void* other, const void* mask, int mask_kind,
+int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const void* mask, int mask_kind,
              long long mask_stride, long long batch, int inverse, int pre, double k0, double two_f, cudaStream_t s) {
     const T sc = inverse ? (T)(1.0 / (double)p->n) : (T)1;
+    {
+        P2Stage<T> st[2] = {p2_stage<T>(AX_ROW, inverse, sc), p2_stage<T>(AX_COL, inverse, sc)};
+        st[0].in = static_cast<const cx<T>*>(in);
+        st[0].out_pre = static_cast<cx<T>*>(state_out);
+        st[0].out_ring = 1;
+        st[0].pre = (pre == PRE_LENS) ? P2_FAC_LENS : P2_FAC_NONE;
+        if (mask != nullptr) { st[0].mask = mask; st[0].mask_kind = mask_kind; st[0].mask_beam_stride = mask_stride; }
+        st[1].in_ring = 1;
+        st[1].out = static_cast<cx<T>*>(other);
+        const int rc = run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s);
+        if (rc >= 0) return rc;
+    }
     {
         StageArgs<T> st[2] = {stage<T>(AX_ROW, inverse, sc), stage<T>(AX_COL, inverse, sc)};
         st[0].in = static_cast<const cx<T>*>(in);
@@ -454,11 +626,23 @@ int mul_fft2(const lp2d_plan* p, const void* in, void* state_out, void* other, c
 }
 
 template <typename T>
-int propagate_state(const lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
+int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
                     cudaStream_t s) {
     const T sc = (T)(1.0 / (double)p->n);
     {
         // rows: spectrum *= H (state stored back), inverse row transform -> ring; columns: inverse -> field
+        P2Stage<T> st[2] = {p2_stage<T>(AX_ROW, 1, sc), p2_stage<T>(AX_COL, 1, sc)};
+        st[0].in = static_cast<const cx<T>*>(spectrum);
+        st[0].out_pre = static_cast<cx<T>*>(spectrum);
+        st[0].pre = P2_FAC_H;
+        st[0].out_ring = 1;
+        st[1].in_ring = 1;
+        st[1].out = static_cast<cx<T>*>(field);
+        st[1].inten = static_cast<T*>(intensity);
+        const int rc = run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s);
+        if (rc >= 0) return rc;
+    }
+    {
         StageArgs<T> st[2] = {stage<T>(AX_ROW, 1, sc), stage<T>(AX_COL, 1, sc)};
         st[0].in = static_cast<const cx<T>*>(spectrum);
         st[0].out_pre = static_cast<cx<T>*>(spectrum);
@@ -499,10 +683,23 @@ int propagate_state(const lp2d_plan* p, void* spectrum, void* field, void* inten
 }
 
 template <typename T>
-int propagate_fresh(const lp2d_plan* p, const void* fin, void* fout, void* spec_out, void* intensity, void* work,
+int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, void* intensity, void* work,
                     long long work_bytes, long long batch, double z, cudaStream_t s) {
     {
         // forward rows -> ring; columns: FFT, H, inverse FFT in the ring; inverse rows -> field / |E|^2
+        const T inv_n = (T)(1.0 / (double)p->n);
+        P2Stage<T> st[3] = {p2_stage<T>(AX_ROW, 0, (T)1), p2_stage<T>(AX_COL, 0, inv_n), p2_stage<T>(AX_ROW, 1, inv_n)};
+        st[0].in = static_cast<const cx<T>*>(fin);
+        st[0].out_ring = 1;
+        st[1].in_ring = 1; st[1].out_ring = 1; st[1].mid = 1;
+        st[1].out_mid = static_cast<cx<T>*>(spec_out);
+        st[2].in_ring = 1;
+        st[2].out = static_cast<cx<T>*>(fout);
+        st[2].inten = static_cast<T*>(intensity);
+        const int rc = run_p2<T>(p, st, 3, P2_FAC_H, 1, z, 0.0, batch, s);
+        if (rc >= 0) return rc;
+    }
+    {
         const T inv_n = (T)(1.0 / (double)p->n);
         StageArgs<T> st[3] = {stage<T>(AX_ROW, 0, (T)1), stage<T>(AX_COL, 0, inv_n), stage<T>(AX_ROW, 1, inv_n)};
         st[0].in = static_cast<const cx<T>*>(fin);

@@ -1,0 +1,25 @@
+// complex64 instances of the fused step kernel: (N, E, lines per CTA, min CTAs/SM)
+#define LP2D_PACKED_F32 1
+#include "pipe2_ops.cuh"
+
+namespace lp2d {
+static const P2Ops<float> kP2F32[] = {
+    P2Inst<float, 1024, 32, 4, 4>::entry(),
+};
+const P2Ops<float>* find_p2_f32(int n, int variant) {
+    const P2Ops<float>* first = nullptr;
+    int seen = 0;
+    for (const auto& o : kP2F32) {
+        if (o.n != n) continue;
+        if (seen++ == variant) return &o;
+        if (first == nullptr) first = &o;
+    }
+    return first;
+}
+cudaError_t p2_factor_plane_f32(float2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+                                double k0, double two_f, cudaStream_t s) {
+    factor_plane_kernel<float><<<148 * 4, 256, 0, s>>>(fac, tabs, tabs + n, tabs + 2 * n, n, fl, kind, by_column, z, k0, two_f);
+    ++g_launches;
+    return cudaGetLastError();
+}
+}  // namespace lp2d

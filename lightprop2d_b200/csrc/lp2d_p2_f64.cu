@@ -1,0 +1,24 @@
+// complex128 instances of the fused step kernel: (N, E, lines per CTA, min CTAs/SM)
+#include "pipe2_ops.cuh"
+
+namespace lp2d {
+static const P2Ops<double> kP2F64[] = {
+    P2Inst<double, 1024, 16, 2, 4>::entry(),
+};
+const P2Ops<double>* find_p2_f64(int n, int variant) {
+    const P2Ops<double>* first = nullptr;
+    int seen = 0;
+    for (const auto& o : kP2F64) {
+        if (o.n != n) continue;
+        if (seen++ == variant) return &o;
+        if (first == nullptr) first = &o;
+    }
+    return first;
+}
+cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+                                double k0, double two_f, cudaStream_t s) {
+    factor_plane_kernel<double><<<148 * 4, 256, 0, s>>>(fac, tabs, tabs + n, tabs + 2 * n, n, fl, kind, by_column, z, k0, two_f);
+    ++g_launches;
+    return cudaGetLastError();
+}
+}  // namespace lp2d

@@ -1,0 +1,86 @@
+// Host-side entry of one (T, N, E, W) instance of the fused step kernel (pipe2.cuh).
+#pragma once
+#include <cmath>
+#include <cuda_runtime.h>
+#include <vector>
+#include "pipe2.cuh"
+
+namespace lp2d {
+
+template <typename T>
+struct P2Ops {
+    int n, e, w;
+    int tiles;          // items per (stage, group)
+    int threads;
+    int fl;             // factor-plane row stride (samples)
+    int tw_size;        // twiddle table entries of LinePlan<n, e>
+    size_t smem_x;      // exchange / landing area
+    size_t smem_f;      // factor rows, only for steps that need them
+    // win_ptr / win_bytes: optional L2 persisting access window (the ring); win_bytes = 0: none
+    cudaError_t (*launch)(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void* win_ptr,
+                          size_t win_bytes);
+    // opt in to large dynamic shared memory; resident CTAs per SM with / without the factor rows
+    cudaError_t (*configure)(int* ctas_per_sm_factor, int* ctas_per_sm_plain);
+    void (*twiddles)(std::vector<double>& re_im);
+};
+
+const P2Ops<float>* find_p2_f32(int n, int variant);
+const P2Ops<double>* find_p2_f64(int n, int variant);
+cudaError_t p2_factor_plane_f32(float2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+                                double k0, double two_f, cudaStream_t s);
+cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+                                double k0, double two_f, cudaStream_t s);
+
+extern long long g_launches;
+
+template <typename T, int N, int E, int W, int MINB>
+struct P2Inst {
+    using K = P2Cfg<T, N, E, W>;
+    using LP = LinePlan<N, E>;
+    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void* win_ptr,
+                              size_t win_bytes) {
+        const size_t smem = K::SMEM_X + (need_factor ? K::SMEM_F : 0);
+        ++g_launches;
+        if (win_bytes == 0) {
+            p2_kernel<T, N, E, W, MINB><<<grid, K::THREADS, smem, s>>>(a);
+            return cudaGetLastError();
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = win_ptr;
+        attr[0].val.accessPolicyWindow.num_bytes = win_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, p2_kernel<T, N, E, W, MINB>, a);
+    }
+    static cudaError_t configure(int* with_factor, int* plain) {
+        auto kern = p2_kernel<T, N, E, W, MINB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K::SMEM_X + K::SMEM_F));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X + K::SMEM_F);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
+    }
+    static void twiddles(std::vector<double>& w) {
+        w.assign(2 * (size_t)LP::tw_size(), 0.0);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int p = 1; p < LP::npass(); ++p) {
+            const int R = LP::radix(p), Ns = LP::ns(p), off = LP::tw_offset(p);
+            for (int r = 1; r < R; ++r)
+                for (int k = 0; k < Ns; ++k) {
+                    const long double ang = -two_pi * (long double)((long long)k * r) / (long double)((long long)Ns * R);
+                    w[2 * (size_t)(off + (r - 1) * Ns + k)] = (double)cosl(ang);
+                    w[2 * (size_t)(off + (r - 1) * Ns + k) + 1] = (double)sinl(ang);
+                }
+        }
+    }
+    static constexpr P2Ops<T> entry() {
+        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles};
+    }
+};
+
+}  // namespace lp2d

@@ -24,6 +24,8 @@ def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     print(torch.cuda.get_device_name(0), flush=True)
     sizes = [16, 32, 64, 128, 256, 512, 1024, 2048] + ([] if quick else [4096])
+    if os.environ.get("LP2D_SELFTEST_SIZES"):
+        sizes = [int(v) for v in os.environ["LP2D_SELFTEST_SIZES"].split(",")]
     bad = 0
     for bits in (64, 128):
         tol = 1e-5 if bits == 64 else 1e-12
@@ -32,7 +34,7 @@ def main():
             if bits == 128 and n > 4096:
                 continue
             rng = np.random.default_rng(n + bits)
-            B = 2 if n <= 1024 else 1
+            B = int(os.environ.get("LP2D_SELFTEST_BATCH", 2 if n <= 1024 else 1))
             f0 = (rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))).astype(ct)
             area, wl = 200 * um * n / 256, 632 * nm
             z = 100 * um

@@ -11,13 +11,15 @@ def raw(path, idx=0):
         if 'issue_stalled' in h and 'per_issue_active.ratio' in h:
             try:
                 if float(v) > 0.1:
-                    print(f"  {h[35:-29]:28s} {float(v):6.2f}")
+                    print(f"  {h.split('issue_stalled_')[1].split('_per_issue')[0]:28s} {float(v):6.2f}")
             except ValueError:
                 pass
 
 
-def source(path, top=25):
+def source(path, top=25, seg=0):
     rows = list(csv.reader(open(path)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    rows = rows[starts[seg]:starts[seg + 1]]
     hdr = rows[1]; data = rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
     stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
@@ -40,8 +42,24 @@ def source(path, top=25):
         print(f"{op:18s} n={opn[op]:4d} exec={opex[op]/totex*100:5.1f}% samples={s/tot*100:5.1f}%  {t3}")
 
 
+def lines(path, seg=0, top=22):
+    rows = list(csv.reader(open(path)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    rows = rows[starts[seg]:starts[seg + 1]]
+    hdr = rows[1]; data = rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    st = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
+    tot = sum(int(r[ix['# Samples']]) for r in data if len(r) > ix['stall_wait'])
+    best = sorted([r for r in data if len(r) > ix['stall_wait']], key=lambda r: -int(r[ix['# Samples']]))[:top]
+    for r in best:
+        d = {k: int(r[ix[k]]) for k in st}
+        t2 = ', '.join(f"{k[6:]}={v}" for k, v in sorted(d.items(), key=lambda kv: -kv[1])[:2])
+        print(f"{int(r[ix['# Samples']])/tot*100:5.1f}% ex={r[ix['Instructions Executed']]:>9s} {r[ix['Source']][:58]:58s} {t2}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "raw":
         raw(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     else:
-        source(sys.argv[2])
+        source(sys.argv[2], 25, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+        lines(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
