@@ -252,30 +252,44 @@ def run_ours(args):
     t_col = time_pass(lambda: lib.lp2d_pass(plan, _lib.AXIS_COLS, _lib.OP_FFT, fld.data_ptr(), fld.data_ptr(),
                                             None, None, B, 1, 0.0, st))
     row_bytes, col_bytes = 3 * PB * B, 2 * PB * B
-    dominant = "row" if t_row >= t_col else "col"
-    dom_t, dom_bytes = (t_row, row_bytes) if dominant == "row" else (t_col, col_bytes)
-    achieved = dom_bytes / (dom_t * 1e-3) / 1e9
     step_ms = ms / K
     step_alg = 3 * PB * B                                    # read S, write S, write field
+    name_buf = C.create_string_buffer(200)
+    fused = lib.lp2d_plan_step_kernel(plan, name_buf, 200) == 1
+    per_pass = {"row_pass_ms": t_row, "col_pass_ms": t_col,
+                "row_pass_frac": row_bytes / (t_row * 1e-3) / 1e9 / peak, "col_pass_frac": col_bytes / (t_col * 1e-3) / 1e9 / peak,
+                "note": "one-kernel-per-pass line kernels timed alone (row: 3*P*B, column: 2*P*B of their own traffic); "
+                        "they serve plain fft2 and the fresh chain, and every step when LP2D_PIPE=0"}
+    if fused:
+        # ONE launch per step: the dominant kernel is the step itself; time it alone
+        t_step = time_pass(lambda: lib.lp2d_propagate(plan, spec.data_ptr(), fld.data_ptr(), None, B, DZ, st))
+        dominant, dom_t, dom_bytes = "step", t_step, step_alg
+        kernel_name = name_buf.value.decode()
+    else:
+        dominant = "row" if t_row >= t_col else "col"
+        dom_t, dom_bytes = (t_row, row_bytes) if dominant == "row" else (t_col, col_bytes)
+        kernel_name = ("line_kernel<row, PRE_H> (spectrum*=H, store spectrum, inverse row FFT)" if dominant == "row"
+                       else "line_kernel<col> (inverse column FFT in place)")
+    achieved = dom_bytes / (dom_t * 1e-3) / 1e9
     roofline = {
         "bound": "hbm",
-        "kernel": ("line_kernel<row, PRE_H> (spectrum*=H, store spectrum, inverse row FFT)" if dominant == "row"
-                   else "line_kernel<col> (inverse column FFT in place)"),
+        "kernel": kernel_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes,
-        "kernel_ms": {"row_pass": t_row, "col_pass": t_col},
+        "kernel_ms": dom_t,
+        "per_pass_kernels": per_pass,
         "step": {"algorithmic_bytes": step_alg, "achieved": step_alg / (step_ms * 1e-3) / 1e9,
                  "frac": step_alg / (step_ms * 1e-3) / 1e9 / peak,
-                 "note": "whole propagate step (both kernels) against 3*N^2*8 B per beam"},
+                 "note": "whole propagate step in the timed loop against 3*N^2*8 B per beam (read spectrum, write spectrum, write field)"},
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as f:
                 tj = json.load(f)
-            roofline["traffic"] = tj.get(dominant + "_pass_bytes_per_beam", 0) * B or None
+            roofline["traffic"] = tj.get(dominant + "_bytes_per_beam", tj.get(dominant + "_pass_bytes_per_beam", 0)) * B or None
             roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass

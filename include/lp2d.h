@@ -154,6 +154,12 @@ LP2D_API int lp2d_modes_project(int dtype, const void* field, const void* modes,
 LP2D_API int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void* field, int n,
                           int nb, int nmodes, long long batch, void* stream);
 
+/* Which kernel family serves the steps of this plan that read and write state (propagate, lens,
+ * mask + fft2): 0 = one kernel per pass (row pass, column pass), 1 = the fused step kernel (one
+ * launch per step, row <-> column intermediate in an L2-resident ring).  `name` (may be NULL)
+ * receives a short description (at most name_len - 1 characters). */
+LP2D_API int lp2d_plan_step_kernel(lp2d_plan* plan, char* name, int name_len);
+
 /* How many kernels this library has launched in this process (for bench accounting). */
 LP2D_API long long lp2d_launch_count(void);
 

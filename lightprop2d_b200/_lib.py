@@ -39,6 +39,7 @@ SIGNATURES = {
     "lp2d_moments": (_i, [_i, _vp, _i, _d, _d, _d, _vp, _vp]),
     "lp2d_modes_project": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
     "lp2d_modes_synthesize": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "lp2d_plan_step_kernel": (_i, [_vp, C.c_char_p, _i]),
     "lp2d_launch_count": (_ll, []),
 }
 

@@ -66,6 +66,8 @@ struct lp2d_plan {
     int pipe_mode;             // 0: persistent CTAs, 1: one CTA per item (ticket)
     int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
     int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
+    int fused_ops;             // which steps use the fused step kernel: 1 plain fft2, 2 steps that store state
+                               // (propagate, lens, mask + fft2), 4 the fresh field -> field chain
     // fused step kernel (pipe2.cuh)
     const P2Ops<float>* p2_32;
     const P2Ops<double>* p2_64;
@@ -186,7 +188,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     // opt-in (LP2D_PIPE=1): it moves only the algorithmic bytes through HBM but is, in this round,
     // not yet faster than the one-kernel-per-pass path ("The persistent pipeline kernel")
     env = getenv("LP2D_PIPE");
-    if (env != nullptr && atoi(env) != 0) {
+    if (env != nullptr && atoi(env) == 1) {
         env = getenv("LP2D_PIPE_VARIANT");
         const int pvar = env ? atoi(env) : 0;
         const PipeOps<float>* q32 = dtype == LP2D_C64 ? find_pipe_f32(n, pvar) : nullptr;
@@ -218,8 +220,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         }
     }
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0;
+    // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
-    if (env != nullptr && atoi(env) == 2) {
+    if (env == nullptr || atoi(env) == 2) {
         env = getenv("LP2D_PIPE_VARIANT");
         const int pvar = env ? atoi(env) : 0;
         const P2Ops<float>* q32 = dtype == LP2D_C64 ? find_p2_f32(n, pvar) : nullptr;
@@ -259,6 +262,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     env = getenv("LP2D_PIPE_SLOTS"); p->pipe_slots = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_GRID");  p->pipe_grid = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_HINTS"); p->pipe_hints = env ? atoi(env) : 3;
+    // measured (profiles/r1c_size_sweep.log): the fused kernel wins on the steps that read AND write state
+    // (3*P*B algorithmic bytes); plain fft2 and the three-stage fresh chain stay on the per-pass kernels
+    env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : 2;
     env = getenv("LP2D_PIPE_PERSIST"); p->pipe_persist = env ? atoi(env) : 0;
     if (p->pipe_persist && p->ring != nullptr) {
         cudaDeviceProp prop;
@@ -271,6 +277,23 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     }
     *out = p;
     return LP2D_OK;
+}
+
+int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
+    if (p == nullptr) return 0;
+    const bool fused = (p->p2_32 != nullptr || p->p2_64 != nullptr) && (p->fused_ops & 2);
+    if (name != nullptr && name_len > 0) {
+        if (fused) {
+            const int e = p->p2_32 ? p->p2_32->e : p->p2_64->e, w = p->p2_32 ? p->p2_32->w : p->p2_64->w;
+            const int kind = p->p2_32 ? p->p2_32->persistent : p->p2_64->persistent;
+            snprintf(name, (size_t)name_len, "%s<%s, N=%d, E=%d, W=%d> fused step (rows -> L2 ring -> columns, one launch)",
+                     kind == 1 ? "p2_kernel" : kind == 2 ? "t4_kernel" : "t3_kernel", p->dtype == LP2D_C64 ? "float" : "double", p->n, e, w);
+        } else {
+            const int e = p->ops32 ? p->ops32->e : p->ops64->e;
+            snprintf(name, (size_t)name_len, "line_kernel<%s, N=%d, E=%d> row pass + column pass", p->dtype == LP2D_C64 ? "float" : "double", p->n, e);
+        }
+    }
+    return fused ? 1 : 0;
 }
 
 int lp2d_plan_destroy(lp2d_plan* p) {
@@ -354,10 +377,11 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     if (p->pipe_grid > 0 && p->pipe_grid < conc) conc = p->pipe_grid;
     const int tiles = ops->tiles;
     long long G = p->pipe_g > 0 ? p->pipe_g : 1;
+    if (ops->persistent == 2) G = 1;
     if (G > batch) G = batch;
     // lag (in groups) between consecutive stages of a group: the items in between cover every resident
     // CTA twice (an item's dependencies are looked at one item ahead of its start)
-    const long long reach = 2 * conc;
+    const long long reach = ops->persistent == 1 ? 2 * conc : (5 * conc) / 4;
     int lag = p->pipe_lag > 0 ? p->pipe_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles));
     if (lag < 1) lag = 1;
     // ring slots (groups): the stage that refills a slot must also be `lag` groups behind the last
@@ -401,7 +425,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "fused step: batch too large for one launch");
         a.total_items = (int)total;
         LP2D_CU(cudaMemsetAsync(p->counters, 0, sizeof(unsigned int) * (1 + (size_t)nstages * a.ngroups), s), "fused step counters");
-        const unsigned grid = (unsigned)(total < conc ? total : conc);
+        const unsigned grid = ops->persistent == 1 ? (unsigned)(total < conc ? total : conc) : (unsigned)total;
         LP2D_CU(ops->launch(a, grid, need_factor, s, p->ring, p->pipe_persist ? (size_t)(slots * G * plane) : 0), "fused step launch");
     }
     return LP2D_OK;
@@ -577,7 +601,7 @@ int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const v
         if (mask != nullptr) { st[0].mask = mask; st[0].mask_kind = mask_kind; st[0].mask_beam_stride = mask_stride; }
         st[1].in_ring = 1;
         st[1].out = static_cast<cx<T>*>(other);
-        const int rc = run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s);
+        const int rc = (p->fused_ops & (state_out != nullptr ? 2 : 1)) ? run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s) : -1;
         if (rc >= 0) return rc;
     }
     {
@@ -639,7 +663,7 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         st[1].in_ring = 1;
         st[1].out = static_cast<cx<T>*>(field);
         st[1].inten = static_cast<T*>(intensity);
-        const int rc = run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s);
+        const int rc = (p->fused_ops & 2) ? run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s) : -1;
         if (rc >= 0) return rc;
     }
     {
@@ -696,7 +720,7 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
         st[2].in_ring = 1;
         st[2].out = static_cast<cx<T>*>(fout);
         st[2].inten = static_cast<T*>(intensity);
-        const int rc = run_p2<T>(p, st, 3, P2_FAC_H, 1, z, 0.0, batch, s);
+        const int rc = (p->fused_ops & 4) ? run_p2<T>(p, st, 3, P2_FAC_H, 1, z, 0.0, batch, s) : -1;
         if (rc >= 0) return rc;
     }
     {

@@ -3,7 +3,10 @@
 
 namespace lp2d {
 static const P2Ops<double> kP2F64[] = {
-    P2Inst<double, 1024, 16, 2, 4>::entry(),
+    T3Inst<double, 512, 16, 4, 3>::entry(),
+    T3Inst<double, 512, 16, 8, 2>::entry(),
+    T3Inst<double, 256, 16, 8, 3>::entry(),
+    T3Inst<double, 256, 8, 8, 4>::entry(),
 };
 const P2Ops<double>* find_p2_f64(int n, int variant) {
     const P2Ops<double>* first = nullptr;

@@ -572,6 +572,316 @@ __global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) p2_kernel(co
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Ticket form of the fused step ("T3"): one CTA per work item instead of a persistent loop, with the
+// register-resident line kernel body of kernels.cuh (global loads straight into registers, E samples
+// per thread, as many resident CTAs as the register file allows).  A CTA draws its item number when
+// it starts (so the numbering follows the real start order), waits until what the item depends on is
+// complete, transforms the tile in the G beams of the group, signals and exits.  Latencies (ticket,
+// dependency poll, global loads) are hidden by the other resident CTAs, exactly as in the
+// one-kernel-per-pass path, while the intermediate lives in the L2-resident ring and the pointwise
+// factor comes from the L2-resident factor plane (no FP64 in this kernel).
+template <typename T, int N, int E, int W>
+struct T3Cfg {
+    using P = LinePlan<N, E>;
+    static constexpr int TPL = P::TPL;
+    static constexpr int THREADS = TPL * W;
+    static constexpr int TILES = N / W;
+    static constexpr int SZ = (int)sizeof(cx<T>);
+    static constexpr int S128 = 128 / SZ;
+    static constexpr int WANT = (W >= S128) ? 1 : S128 / W;
+    static constexpr int LS = P::LINE_SLOTS + ((WANT - P::LINE_SLOTS % S128) + S128) % S128;
+    static constexpr size_t SMEM_X = (P::npass() > 1) ? (size_t)W * LS * SZ : 0;
+    static constexpr int SYNC_ROW = (TPL <= 32) ? SYNC_WARP : ((TPL % 32 == 0 && W <= 15) ? SYNC_NAMED : SYNC_CTA);
+    static constexpr int FL = N / 2 + 2;                   // folded factor row stride (N/2 + 1 used)
+    static_assert(THREADS >= 32 && THREADS <= 1024, "block size");
+};
+
+template <typename T, int N, int E, int W, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+__device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, int tid) {
+    using K = T3Cfg<T, N, E, W>;
+    constexpr int TPL = K::TPL;
+    constexpr long long PLANE = (long long)N * N;
+    constexpr long long PSTRIDE = (AXIS == AX_ROW) ? 1 : N;
+    constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CTA;
+    constexpr bool REV = MID || INV;
+    const P2Stage<T>& st = p.st[S];
+    const int l = (AXIS == AX_ROW) ? tid / TPL : tid % W;
+    const int t = (AXIS == AX_ROW) ? tid % TPL : tid / W;
+    cx<T>* sline = xbuf + l * K::LS;
+    const long long b0 = (long long)it.g * p.G;
+    const long long slot0 = (long long)(it.g % p.ring_slots) * p.G;
+    const long long left = p.nbeams - b0;
+    const int nb = left < p.G ? (int)left : p.G;
+    const int fixed = it.tile * W + l;
+    const long long off0 = (AXIS == AX_ROW) ? (long long)fixed * N : fixed;
+    const long long o_first = (REV ? (long long)((N - t) & (N - 1)) : (long long)t) * PSTRIDE;
+    const long long o_base = (REV ? (long long)(N - t) : (long long)t) * PSTRIDE;
+    constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * PSTRIDE;
+    const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
+    const cx<T>* fline = p.fac + (long long)fixed * K::FL;      // L2-resident factor row of this line
+    const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
+
+    for (int bi = 0; bi < nb; ++bi) {
+        const long long b = b0 + bi;
+        const cx<T>* src = (IN_RING ? p.ring + (slot0 + bi) * PLANE : st.in + b * PLANE) + off0 + t * PSTRIDE;
+        cx<T> v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = IN_RING ? __ldcg(src + (TPL * m) * PSTRIDE) : __ldcs(src + (TPL * m) * PSTRIDE);
+        if constexpr (!IN_RING) {
+            if (st.mask_kind != MASK_NONE) {
+                const long long mb = b * st.mask_beam_stride + off0;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
+            }
+            if (use_pre) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]));
+            }
+            if (st.out_pre != nullptr) {
+                cx<T>* dst = st.out_pre + b * PLANE + off0 + t * PSTRIDE;
+#pragma unroll
+                for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+            }
+        }
+        line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+        if constexpr (MID) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]));
+            if (st.out_mid != nullptr) {
+                cx<T>* dst = st.out_mid + b * PLANE + off0 + t * PSTRIDE;
+#pragma unroll
+                for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+            }
+            line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+        }
+        if (st.scale != (T)1) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cscale(v[m], st.scale);
+        }
+        if constexpr (OUT_RING) {
+            cx<T>* dst = p.ring + (slot0 + bi) * PLANE + off0;
+            if (keep_ring) {
+                p2_st_ring<2>(dst + o_first, v[0]);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) p2_st_ring<2>(dst + m * o_step, v[m]);
+            } else {
+                p2_st_ring<0>(dst + o_first, v[0]);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) p2_st_ring<0>(dst + m * o_step, v[m]);
+            }
+        } else {
+            if (st.out != nullptr) {
+                cx<T>* dst = st.out + b * PLANE + off0;
+                __stcs(dst + o_first, v[0]);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) __stcs(dst + m * o_step, v[m]);
+            }
+            if (st.inten != nullptr) {
+                T* dst = st.inten + b * PLANE + off0;
+                __stcs(dst + o_first, v[0].x * v[0].x + v[0].y * v[0].y);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) __stcs(dst + m * o_step, v[m].x * v[m].x + v[m].y * v[m].y);
+            }
+        }
+    }
+}
+
+template <typename T, int N, int E, int W, int MINB>
+__global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(const __grid_constant__ P2Args<T> p) {
+    using K = T3Cfg<T, N, E, W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_item;
+    cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int item = (int)atomicAdd(&p.counters[0], 1u);
+        P2Item it;
+        if (item < p.total_items && p2_decode<T, K::TILES>(p, item, it)) {
+            while (!p2_ready<T, K::TILES>(p, item, (unsigned)K::TILES)) __nanosleep(100);
+            s_item = item;
+        } else {
+            s_item = -1;
+        }
+    }
+    __syncthreads();
+    const int item = s_item;
+    if (item < 0) return;
+    P2Item it;
+    p2_decode<T, K::TILES>(p, item, it);
+    if (it.s == 0) {
+        if (p.st[0].inverse) t3_item<T, N, E, W, 0, AX_ROW, false, true, false, true>(p, it, xbuf, tid);
+        else t3_item<T, N, E, W, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
+    } else if (it.s == 1) {
+        if (p.st[1].mid) t3_item<T, N, E, W, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
+        else if (p.st[1].inverse) t3_item<T, N, E, W, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
+        else t3_item<T, N, E, W, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
+    } else {
+        t3_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
+    }
+    __syncthreads();                                       // all stores of the item are issued
+    if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+}
+
+// --------------------------------------------------------------------------------------------
+// Ticket form with staged tiles ("T4"): one CTA per work item, an item = TG consecutive tiles of
+// ONE beam.  The first tile is requested as soon as the item is known; every further tile (and its
+// factor rows) is copied by cp.async into the exchange buffer while the previous one is being
+// transformed (from the moment its last gather is done), so one ticket, one dependency poll and one
+// exposed load latency are paid per TG tiles, while the ring still holds one beam per group.
+template <typename T, int N, int E, int W, int TG, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+__device__ __forceinline__ void t4_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, cx<T>* fbuf, int tid) {
+    using K = P2Cfg<T, N, E, W>;
+    constexpr int TPL = K::TPL;
+    constexpr long long PLANE = (long long)N * N;
+    constexpr long long PSTRIDE = (AXIS == AX_ROW) ? 1 : N;
+    constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CTA;
+    constexpr bool REV = MID || INV;
+    const P2Stage<T>& st = p.st[S];
+    const int l = (AXIS == AX_ROW) ? tid / TPL : tid % W;
+    const int t = (AXIS == AX_ROW) ? tid % TPL : tid / W;
+    cx<T>* sline = xbuf + l * K::LS;
+    const cx<T>* fline = fbuf + l * K::FL;
+    const long long b = it.g;                                   // G == 1: group = beam
+    const long long slot = it.g % p.ring_slots;
+    const cx<T>* in_plane = IN_RING ? p.ring + slot * PLANE : st.in + b * PLANE;
+    const long long o_first = (REV ? (long long)((N - t) & (N - 1)) : (long long)t) * PSTRIDE;
+    const long long o_base = (REV ? (long long)(N - t) : (long long)t) * PSTRIDE;
+    constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * PSTRIDE;
+    const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
+    const bool use_fac = use_pre || MID;
+    const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
+    const int tile0 = it.tile * TG;
+
+    auto request = [&](int tile) {
+        if (use_fac) p2_copy_factor<T, N, E, W, AXIS>(fbuf, p.fac, tile, tid);
+        p2_copy_tile_k<T, N, E, W, AXIS, 0>(xbuf, in_plane + (AXIS == AX_ROW ? (long long)tile * W * N : (long long)tile * W), tid);
+        p2_commit();
+    };
+    request(tile0);
+    const cx<T>* land = (AXIS == AX_ROW) ? sline + t : xbuf + t * W + l;
+    for (int k = 0; k < TG; ++k) {
+        const int tile = tile0 + k;
+        const int fixed = tile * W + l;
+        const long long off0 = (AXIS == AX_ROW) ? (long long)fixed * N : fixed;
+        p2_wait_all();
+        line_sync<SYNC, TPL>(l);
+        cx<T> v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = land[(AXIS == AX_ROW) ? TPL * m : TPL * m * W];
+        if constexpr (!IN_RING) {
+            if (st.mask_kind != MASK_NONE) {
+                const long long mb = b * st.mask_beam_stride + off0;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
+            }
+            if (use_pre) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]);
+            }
+            if (st.out_pre != nullptr) {
+                cx<T>* dst = st.out_pre + b * PLANE + off0 + t * PSTRIDE;
+#pragma unroll
+                for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+            }
+        }
+        auto hook = [&]() {
+            if (k + 1 < TG) {
+                line_sync<SYNC, TPL>(l);                        // every gather of this line / tile is done
+                request(tile + 1);
+            }
+        };
+        if constexpr (MID) {
+            P2NoHook none;
+            p2_fft<T, N, E, SYNC, P2NoHook>(v, sline, p.tw, t, l, none);
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]);
+            if (st.out_mid != nullptr) {
+                cx<T>* dst = st.out_mid + b * PLANE + off0 + t * PSTRIDE;
+#pragma unroll
+                for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+            }
+        }
+        p2_fft<T, N, E, SYNC, decltype(hook)>(v, sline, p.tw, t, l, hook);
+        if (st.scale != (T)1) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cscale(v[m], st.scale);
+        }
+        if constexpr (OUT_RING) {
+            cx<T>* dst = p.ring + slot * PLANE + off0;
+            if (keep_ring) {
+                p2_st_ring<2>(dst + o_first, v[0]);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) p2_st_ring<2>(dst + m * o_step, v[m]);
+            } else {
+                p2_st_ring<0>(dst + o_first, v[0]);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) p2_st_ring<0>(dst + m * o_step, v[m]);
+            }
+        } else {
+            if (st.out != nullptr) {
+                cx<T>* dst = st.out + b * PLANE + off0;
+                __stcs(dst + o_first, v[0]);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) __stcs(dst + m * o_step, v[m]);
+            }
+            if (st.inten != nullptr) {
+                T* dst = st.inten + b * PLANE + off0;
+                __stcs(dst + o_first, v[0].x * v[0].x + v[0].y * v[0].y);
+                dst += o_base;
+#pragma unroll
+                for (int m = 1; m < E; ++m) __stcs(dst + m * o_step, v[m].x * v[m].x + v[m].y * v[m].y);
+            }
+        }
+    }
+}
+
+template <typename T, int N, int E, int W, int TG, int MINB>
+__global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) t4_kernel(const __grid_constant__ P2Args<T> p) {
+    using K = P2Cfg<T, N, E, W>;
+    constexpr int ITEMS = K::TILES / TG;                    // items per (stage, beam)
+    static_assert(K::TILES % TG == 0, "tile group");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_item;
+    cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* fbuf = reinterpret_cast<cx<T>*>(smem_raw + K::SMEM_X);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int item = (int)atomicAdd(&p.counters[0], 1u);
+        P2Item it;
+        if (item < p.total_items && p2_decode<T, ITEMS>(p, item, it)) {
+            while (!p2_ready<T, ITEMS>(p, item, (unsigned)ITEMS)) __nanosleep(100);
+            s_item = item;
+        } else {
+            s_item = -1;
+        }
+    }
+    __syncthreads();
+    const int item = s_item;
+    if (item < 0) return;
+    P2Item it;
+    p2_decode<T, ITEMS>(p, item, it);
+    if (it.s == 0) {
+        if (p.st[0].inverse) t4_item<T, N, E, W, TG, 0, AX_ROW, false, true, false, true>(p, it, xbuf, fbuf, tid);
+        else t4_item<T, N, E, W, TG, 0, AX_ROW, false, true, false, false>(p, it, xbuf, fbuf, tid);
+    } else if (it.s == 1) {
+        if (p.st[1].mid) t4_item<T, N, E, W, TG, 1, AX_COL, true, true, true, false>(p, it, xbuf, fbuf, tid);
+        else if (p.st[1].inverse) t4_item<T, N, E, W, TG, 1, AX_COL, true, false, false, true>(p, it, xbuf, fbuf, tid);
+        else t4_item<T, N, E, W, TG, 1, AX_COL, true, false, false, false>(p, it, xbuf, fbuf, tid);
+    } else {
+        t4_item<T, N, E, W, TG, 2, AX_ROW, true, false, false, true>(p, it, xbuf, fbuf, tid);
+    }
+    __syncthreads();                                       // all stores of the item are issued
+    if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+}
+
 // The factor plane: fac[line][idx], idx = 0 .. N/2 (row stride FL).
 //   kind P2_FAC_H, by_column = 0: line = row j,    fac = H(a[idx], b[j])      (a[i] == a[N - i] bit for bit)
 //   kind P2_FAC_H, by_column = 1: line = column i, fac = H(a[i], b[idx])

@@ -22,6 +22,7 @@ struct P2Ops {
     // opt in to large dynamic shared memory; resident CTAs per SM with / without the factor rows
     cudaError_t (*configure)(int* ctas_per_sm_factor, int* ctas_per_sm_plain);
     void (*twiddles)(std::vector<double>& re_im);
+    int persistent;     // 1: p2_kernel (grid = resident CTAs), 0: t3_kernel, 2: t4_kernel (grid = items, G = 1)
 };
 
 const P2Ops<float>* find_p2_f32(int n, int variant);
@@ -32,6 +33,70 @@ cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl,
                                 double k0, double two_f, cudaStream_t s);
 
 extern long long g_launches;
+
+// exp(-2 pi i k r / (Ns R)) for every pass after the first of the schedule LP, FP64 re/im interleaved
+template <typename LP>
+void p2_twiddles(std::vector<double>& w) {
+    w.assign(2 * (size_t)LP::tw_size(), 0.0);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int p = 1; p < LP::npass(); ++p) {
+        const int R = LP::radix(p), Ns = LP::ns(p), off = LP::tw_offset(p);
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                const long double ang = -two_pi * (long double)((long long)k * r) / (long double)((long long)Ns * R);
+                w[2 * (size_t)(off + (r - 1) * Ns + k)] = (double)cosl(ang);
+                w[2 * (size_t)(off + (r - 1) * Ns + k) + 1] = (double)sinl(ang);
+            }
+    }
+}
+
+// ticket form (t3_kernel): same P2Ops record; grid = number of items (flagged by persistent = 0)
+template <typename T, int N, int E, int W, int MINB>
+struct T3Inst {
+    using K = T3Cfg<T, N, E, W>;
+    using LP = LinePlan<N, E>;
+    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool, cudaStream_t s, void*, size_t) {
+        t3_kernel<T, N, E, W, MINB><<<grid, K::THREADS, K::SMEM_X, s>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t configure(int* with_factor, int* plain) {
+        auto kern = t3_kernel<T, N, E, W, MINB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_X);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X);
+        *plain = *with_factor;
+        return e;
+    }
+    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
+    static constexpr P2Ops<T> entry() {
+        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, 0, &launch, &configure, &twiddles, 0};
+    }
+};
+
+// ticket form with staged tiles (t4_kernel): items of TG tiles of one beam (G is forced to 1)
+template <typename T, int N, int E, int W, int TG, int MINB>
+struct T4Inst {
+    using K = P2Cfg<T, N, E, W>;
+    using LP = LinePlan<N, E>;
+    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void*, size_t) {
+        t4_kernel<T, N, E, W, TG, MINB><<<grid, K::THREADS, K::SMEM_X + (need_factor ? K::SMEM_F : 0), s>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t configure(int* with_factor, int* plain) {
+        auto kern = t4_kernel<T, N, E, W, TG, MINB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K::SMEM_X + K::SMEM_F));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X + K::SMEM_F);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
+    }
+    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
+    static constexpr P2Ops<T> entry() {
+        return P2Ops<T>{N, E, W, K::TILES / TG, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles, 2};
+    }
+};
 
 template <typename T, int N, int E, int W, int MINB>
 struct P2Inst {
@@ -65,21 +130,9 @@ struct P2Inst {
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
     }
-    static void twiddles(std::vector<double>& w) {
-        w.assign(2 * (size_t)LP::tw_size(), 0.0);
-        const long double two_pi = 6.283185307179586476925286766559005768L;
-        for (int p = 1; p < LP::npass(); ++p) {
-            const int R = LP::radix(p), Ns = LP::ns(p), off = LP::tw_offset(p);
-            for (int r = 1; r < R; ++r)
-                for (int k = 0; k < Ns; ++k) {
-                    const long double ang = -two_pi * (long double)((long long)k * r) / (long double)((long long)Ns * R);
-                    w[2 * (size_t)(off + (r - 1) * Ns + k)] = (double)cosl(ang);
-                    w[2 * (size_t)(off + (r - 1) * Ns + k) + 1] = (double)sinl(ang);
-                }
-        }
-    }
+    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
     static constexpr P2Ops<T> entry() {
-        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles};
+        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles, 1};
     }
 };
 

@@ -45,7 +45,7 @@ def main():
     print(f"n={n} bits={bits} batch={batch}; us/beam (fraction of {hbm/1e9:.0f} GB/s on algorithmic bytes)")
     print(" ".join(f"{k:>6s}" for k in keys) + " | fft2(2PB) | stateful(3PB) | fresh f->f(2PB)")
     envname = {"G": "LP2D_PIPE_G", "LAG": "LP2D_PIPE_LAG", "SLOTS": "LP2D_PIPE_SLOTS", "GRID": "LP2D_PIPE_GRID",
-               "RING": "LP2D_RING_MB", "PIPE": "LP2D_PIPE", "VAR": "LP2D_PIPE_VARIANT", "MODE": "LP2D_PIPE_MODE", "HINTS": "LP2D_PIPE_HINTS", "PERSIST": "LP2D_PIPE_PERSIST"}
+               "RING": "LP2D_RING_MB", "PIPE": "LP2D_PIPE", "VAR": "LP2D_PIPE_VARIANT", "MODE": "LP2D_PIPE_MODE", "HINTS": "LP2D_PIPE_HINTS", "PERSIST": "LP2D_PIPE_PERSIST", "OPS": "LP2D_FUSED_OPS"}
     for combo in itertools.product(*vals):
         for k, v in zip(keys, combo):
             os.environ[envname[k]] = v
