@@ -122,6 +122,20 @@ LP2D_API int lp2d_mul_fft2(lp2d_plan* plan, void* data, void* other, const void*
 LP2D_API int lp2d_pass(lp2d_plan* plan, int axis, int op, const void* in, void* out, void* out_state,
               void* intensity, long long batch, int inverse, double z, void* stream);
 
+/* Row pass over a SLAB of one plane: lines line0 .. line0 + nlines - 1 of an n x n plane, for the
+ * slab-decomposed grid (one row slab per GPU, all-to-all transpose between the two passes; the
+ * second pass runs on the transposed slab with a plan built from lp2d_grid_tables' a/b tables
+ * swapped and negated, see lightprop2d_b200/slab.py).  `in`, `out`, `out_state`, `intensity` point
+ * at the first line OF THE SLAB (line0), not of the plane.  op: LP2D_OP_FFT or LP2D_OP_H_FFT. */
+LP2D_API int lp2d_pass_lines(lp2d_plan* plan, int op, const void* in, void* out, void* out_state,
+                    void* intensity, int line0, int nlines, int inverse, double z, void* stream);
+
+/* Transposing tile pack for the slab exchange: in is a (rows x ld) row-major slab; for every tile
+ * c (0 .. ntiles-1) of `tile` columns, out[c] (tile x rows, contiguous) = transpose(in[:, c*tile :
+ * (c+1)*tile]).  ntiles * tile == ld. */
+LP2D_API int lp2d_pack_transpose(int dtype, const void* in, void* out, int rows, int ld, int tile,
+                        void* stream);
+
 /* iprofile (beam2d.py:717): out = |field|^2 (float for complex64, double for complex128). */
 LP2D_API int lp2d_intensity(lp2d_plan* plan, const void* field, void* out, long long batch, void* stream);
 

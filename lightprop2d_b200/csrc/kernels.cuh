@@ -55,6 +55,7 @@ struct LineArgs {
     T scale;                // applied to the output of the transform
     long long beam_stride;  // samples between consecutive beams (N*N)
     long long mask_beam_stride;  // 0: one mask for every beam
+    int line0;              // rows only: global index of the first line of the launch (slab passes), else 0
     int nlines;             // lines (rows) or column tiles in ONE group
     int groups;             // beam groups a CTA walks over (>= 1)
     long long group_beams;  // beams per group
@@ -156,8 +157,8 @@ line_kernel(const LineArgs<T> p) {
     int fixed;
     bool in_range;
     if constexpr (AXIS == AX_ROW) {
-        const long long line = (long long)blockIdx.x * W + l;
-        in_range = line < p.nlines;
+        const long long line = (long long)blockIdx.x * W + l + p.line0;
+        in_range = line < (long long)p.line0 + p.nlines;
         beam = line / N;
         fixed = (int)(line % N);                              // row j
         base = beam * p.beam_stride + (long long)fixed * N;

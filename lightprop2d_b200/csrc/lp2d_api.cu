@@ -874,6 +874,34 @@ int lp2d_pass(lp2d_plan* p, int axis, int op, const void* in, void* out, void* o
 #undef LP2D_PASS_BODY
 }
 
+int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_state, void* intensity, int line0,
+                    int nlines, int inverse, double z, void* stream) {
+    LP2D_CHECK_PLAN(p);
+    if (in == nullptr || nlines < 0 || line0 < 0 || line0 + nlines > p->n) return fail(LP2D_EINVAL, "pass_lines: bad arguments");
+    if (op != LP2D_OP_FFT && op != LP2D_OP_H_FFT) return fail(LP2D_EINVAL, "pass_lines: op must be LP2D_OP_FFT or LP2D_OP_H_FFT");
+    if (nlines == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double sc = inverse ? 1.0 / (double)p->n : 1.0;
+    const long long back = (long long)line0 * p->n;      // the kernel indexes from line 0 of the plane
+#define LP2D_LINES_BODY(T)                                                                        \
+    {                                                                                             \
+        LineArgs<T> a = base_args<T>(p);                                                          \
+        a.in = static_cast<const cx<T>*>(in) - back;                                              \
+        a.out = out ? static_cast<cx<T>*>(out) - back : nullptr;                                  \
+        a.out_pre = out_state ? static_cast<cx<T>*>(out_state) - back : nullptr;                  \
+        a.inten = intensity ? static_cast<T*>(intensity) - back : nullptr;                        \
+        a.flags = inverse ? F_INVERSE : 0;                                                        \
+        a.scale = (T)sc;                                                                          \
+        a.z = z;                                                                                  \
+        a.groups = 1; a.group_beams = 1; a.nbeams = 1;                                            \
+        a.line0 = line0; a.nlines = nlines;                                                       \
+        LP2D_CU(ops_of<T>(p)->row(op == LP2D_OP_H_FFT ? PRE_H : PRE_NONE, a, s), "slab row pass launch"); \
+        return LP2D_OK;                                                                           \
+    }
+    if (p->dtype == LP2D_C64) LP2D_LINES_BODY(float) else LP2D_LINES_BODY(double)
+#undef LP2D_LINES_BODY
+}
+
 int lp2d_intensity(lp2d_plan* p, const void* field, void* out, long long batch, void* stream) {
     LP2D_CHECK_PLAN(p);
     if (field == nullptr || out == nullptr || batch < 0) return fail(LP2D_EINVAL, "intensity: NULL pointer or negative batch");

@@ -26,6 +26,26 @@ __global__ void expand_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ 
     }
 }
 
+// Transposing tile pack of the slab exchange: out[c][i][r] = in[r][c*tile + i].  32 x 32 samples per
+// CTA through padded shared memory, coalesced on both sides.
+template <typename T>
+__global__ void pack_transpose_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int rows, int ld, int tile) {
+    __shared__ cx<T> s[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;          // column / row origin of this 32 x 32 block
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int r = r0 + k, c = c0 + threadIdx.x;
+        if (r < rows && c < ld) s[k][threadIdx.x] = in[(long long)r * ld + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int c = c0 + k, r = r0 + threadIdx.x;                // output row = input column
+        if (r < rows && c < ld) {
+            const int t = c / tile, i = c - t * tile;
+            out[((long long)t * tile + i) * rows + r] = s[threadIdx.x][k];
+        }
+    }
+}
+
 // out[b][r][c] = mean of the m x m block                  (beam2d.py:456-459)
 template <typename T>
 __global__ void coarse_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int n_in, int m,
@@ -187,6 +207,23 @@ int lp2d_expand(int dtype, const void* in, void* out, int n_in, int n_out, long 
     else
         expand_kernel<double><<<grid_for(total, 256), 256, 0, s>>>((const double2*)in, (double2*)out, n_in, n_out, total);
     return done("expand launch");
+}
+
+int lp2d_pack_transpose(int dtype, const void* in, void* out, int rows, int ld, int tile, void* stream) {
+    if (in == nullptr || out == nullptr || rows <= 0 || ld <= 0 || tile <= 0 || ld % tile != 0 || in == out)
+        return set_error(LP2D_EINVAL, "pack_transpose: bad arguments (tile must divide ld, buffers distinct)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+    if (dtype == LP2D_C64)
+        pack_transpose_kernel<float><<<grid, block, 0, s>>>(static_cast<const float2*>(in), static_cast<float2*>(out), rows, ld, tile);
+    else if (dtype == LP2D_C128)
+        pack_transpose_kernel<double><<<grid, block, 0, s>>>(static_cast<const double2*>(in), static_cast<double2*>(out), rows, ld, tile);
+    else
+        return set_error(LP2D_EINVAL, "pack_transpose: unknown dtype");
+    ++g_launches;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("pack_transpose launch: ") + cudaGetErrorString(e));
+    return LP2D_OK;
 }
 
 int lp2d_coarse(int dtype, const void* in, void* out, int n_in, int m, long long batch, void* stream) {

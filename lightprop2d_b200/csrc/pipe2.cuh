@@ -108,7 +108,7 @@ __device__ __forceinline__ void p2_cp16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
-enum { P2_HINT_STREAM_IN = 1, P2_HINT_KEEP_RING = 2, P2_HINT_STREAM_OUT = 4 };
+enum { P2_HINT_STREAM_IN = 1, P2_HINT_KEEP_RING = 2, P2_HINT_STREAM_OUT = 4, P2_HINT_BLOCK_TICKET = 8 };
 // KIND is a compile-time value: a policy selected at run time ends up in a misaligned uniform
 // register pair (ptxas 12.9) and the copy traps as an illegal instruction.
 template <int KIND>     // 0 no hint, 1 evict first, 2 evict last
@@ -190,6 +190,19 @@ __device__ __forceinline__ bool p2_ready(const P2Args<T>& p, int item, unsigned 
     unsigned int pa, pb;
     p2_poll<T, TILES>(p, item, pa, pb, full);
     return pa >= full && pb >= full;
+}
+
+// Wait until the dependencies of `item` are complete.  The wait is bounded: if they do not complete
+// within ~2 s (they are a few microseconds away in a healthy run) the kernel traps instead of hanging
+// the device.
+template <typename T, int TILES>
+__device__ __forceinline__ void p2_wait_ready(const P2Args<T>& p, int item, unsigned int full) {
+    if (p2_ready<T, TILES>(p, item, full)) return;
+    const long long t0 = clock64();
+    while (!p2_ready<T, TILES>(p, item, full)) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
 }
 
 // origin of tile `tile` of beam bi of group g in the input of stage st
@@ -535,7 +548,7 @@ __global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) p2_kernel(co
         if (first >= 0) {
             sc.nxt = p2_next_valid<T, K::TILES>(p, (int)atomicAdd(&p.counters[0], 1u));
             sc.drawn = atomicAdd(&p.counters[0], 1u);
-            while (!p2_ready<T, K::TILES>(p, first, K::FULL)) __nanosleep(64);
+            p2_wait_ready<T, K::TILES>(p, first, K::FULL);
         }
     }
     __syncthreads();
@@ -563,8 +576,7 @@ __global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) p2_kernel(co
         if (next.item < 0) break;
         if (!next.ready) {
             // the completion of the current item has been signalled: waiting here cannot deadlock
-            if (tid == 0)
-                while (!p2_ready<T, K::TILES>(p, next.item, K::FULL)) __nanosleep(64);
+            if (tid == 0) p2_wait_ready<T, K::TILES>(p, next.item, K::FULL);
             __syncthreads();
             p2_prefetch_item<T, N, E, W>(p, next.item, xbuf, fbuf, tid);
         }
@@ -698,19 +710,32 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     __shared__ int s_item;
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        const int item = (int)atomicAdd(&p.counters[0], 1u);
-        P2Item it;
-        if (item < p.total_items && p2_decode<T, K::TILES>(p, item, it)) {
-            while (!p2_ready<T, K::TILES>(p, item, (unsigned)K::TILES)) __nanosleep(100);
-            s_item = item;
-        } else {
-            s_item = -1;
+    // P2_HINT_BLOCK_TICKET: the item number is the block index (CTAs are dispatched in block-index
+    // order), every warp waits for the dependencies and signals completion on its own: no ticket
+    // round trip and no CTA barrier outside the transforms.  Otherwise thread 0 draws a ticket.
+    const bool block_ticket = (p.hints & P2_HINT_BLOCK_TICKET) != 0;
+    int item;
+    if (block_ticket) {
+        item = (int)blockIdx.x;
+        P2Item it0;
+        if (item >= p.total_items || !p2_decode<T, K::TILES>(p, item, it0)) return;
+        if ((tid & 31) == 0) p2_wait_ready<T, K::TILES>(p, item, (unsigned)K::TILES * (K::THREADS / 32));
+        __syncwarp();
+    } else {
+        if (tid == 0) {
+            const int drawn = (int)atomicAdd(&p.counters[0], 1u);
+            P2Item it0;
+            if (drawn < p.total_items && p2_decode<T, K::TILES>(p, drawn, it0)) {
+                p2_wait_ready<T, K::TILES>(p, drawn, (unsigned)K::TILES);
+                s_item = drawn;
+            } else {
+                s_item = -1;
+            }
         }
+        __syncthreads();
+        item = s_item;
+        if (item < 0) return;
     }
-    __syncthreads();
-    const int item = s_item;
-    if (item < 0) return;
     P2Item it;
     p2_decode<T, K::TILES>(p, item, it);
     if (it.s == 0) {
@@ -723,8 +748,13 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     } else {
         t3_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
     }
-    __syncthreads();                                       // all stores of the item are issued
-    if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+    if (block_ticket) {
+        __syncwarp();                                      // this warp's stores are issued
+        if ((tid & 31) == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+    } else {
+        __syncthreads();                                   // all stores of the item are issued
+        if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -857,7 +887,7 @@ __global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) t4_kernel(co
         const int item = (int)atomicAdd(&p.counters[0], 1u);
         P2Item it;
         if (item < p.total_items && p2_decode<T, ITEMS>(p, item, it)) {
-            while (!p2_ready<T, ITEMS>(p, item, (unsigned)ITEMS)) __nanosleep(100);
+            p2_wait_ready<T, ITEMS>(p, item, (unsigned)ITEMS);
             s_item = item;
         } else {
             s_item = -1;

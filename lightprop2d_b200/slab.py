@@ -1,0 +1,202 @@
+"""A single grid decomposed in slabs over several GPUs (BASELINE.json config 4).
+
+The reference has nothing like this -- a grid that does not fit its device simply runs out of
+memory (tests/gaussbeam_performance.py:33-34).  Here rank r of G owns
+
+* the ROW slab of the field: rows ``r*N/G .. (r+1)*N/G - 1`` of the N x N grid, row-major
+  ``(N/G, N)``;
+* the COLUMN slab of the spectrum, stored TRANSPOSED: ``spec_t[i, j] = spectrum[j, r*N/G + i]``,
+  also ``(N/G, N)``, so that a transform along grid columns is again a transform along the
+  contiguous axis (a row pass of the CUDA library).
+
+``fft2``: local row pass -> all-to-all transpose -> local row pass on the transposed slab.
+``propagate(z)`` (beam2d.py:481-490) with the spectrum resident in the transposed layout needs ONE
+exchange: ``spec_t *= H`` and the inverse transform along grid columns are one fused local pass
+(H in the transposed orientation comes from a second plan whose two FP64 tables are swapped and
+negated: ``(-b[pos]) - (-a[line])`` is bit for bit ``a[line] - b[pos]``), then the all-to-all
+transpose back, then the local inverse row pass (optionally with the fused ``|E|^2``).
+
+The exchange is the only collective: ``torch.distributed.all_to_all_single`` (NCCL over
+NVLink / NVSwitch on GPUs) of G tiles of ``(N/G)^2`` samples per rank; tiles are transposed while
+they are packed (``lp2d_pack_transpose``), the unpack is one strided copy.
+
+The line passes come from a small backend object so that the partitioning / exchange logic can be
+exercised on CPU with the gloo backend (tests/test_dist_gloo.py substitutes a numpy backend; the
+product backend below is CUDA only and raises without a device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def slab_rows(npoints: int, rank: int, world: int):
+    """[start, stop) of the grid rows (or columns) owned by ``rank``; ``world`` must divide ``npoints``."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    if npoints % world:
+        raise ValueError(f"npoints={npoints} is not divisible by the number of slabs {world}")
+    nb = npoints // world
+    return rank * nb, (rank + 1) * nb
+
+
+def kz2_tables(area_size: float, npoints: int, wl: float):
+    """``a[i] = k0^2 - Kx[i]^2``, ``b[j] = Ky[j]^2``, ``x2[i] = X[i]^2`` with the reference's expressions
+    (beam2d.py:299-308) -- the same tables ``Beam2D`` uploads."""
+    dL = area_size / npoints
+    X = np.arange(-npoints // 2, npoints // 2, 1) * dL
+    k0 = 1 / wl
+    Kx = np.fft.fftfreq(npoints, d=dL)
+    return k0 ** 2 - Kx ** 2, Kx ** 2, X ** 2
+
+
+class CudaLineBackend:
+    """Row passes and the transposing pack of liblp2d.so on the current CUDA device."""
+
+    def __init__(self, area_size, npoints, wl, complex_bits, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("the slab-decomposed grid needs a CUDA device (there is no CPU fallback)")
+        from .beam2d import _Plan
+        self.torch = torch
+        self.lib = _lib.load()
+        self.n, self.bits = int(npoints), complex_bits
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.cdtype = torch.complex64 if complex_bits == 64 else torch.complex128
+        self.rdtype = torch.float32 if complex_bits == 64 else torch.float64
+        a, b, x2 = kz2_tables(area_size, npoints, wl)
+        with torch.cuda.device(self.device):
+            self.plan = _Plan(npoints, complex_bits, a, b, x2)
+            # transposed orientation: line = grid column i, position = grid row j
+            self.plan_t = _Plan(npoints, complex_bits, -b, -a, x2)
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, *shape, real=False):
+        return self.torch.empty(*shape, dtype=self.rdtype if real else self.cdtype, device=f"cuda:{self.device}")
+
+    def lines(self, x, line0, inverse=False, transposed=False, z=None, state_out=None, intensity=None, out=None):
+        """(i)FFT along the last axis of the slab ``x`` (lines line0 .. line0 + rows - 1 of the plane).
+        With ``z``: x *= H(z) first (H in the slab's orientation), the product goes to ``state_out``."""
+        plan = self.plan_t if transposed else self.plan
+        out = self.empty(*x.shape) if out is None else out
+        op = _lib.OP_FFT if z is None else _lib.OP_H_FFT
+        _lib.check(self.lib.lp2d_pass_lines(plan.handle, op, x.data_ptr(), out.data_ptr(),
+                                            None if state_out is None else state_out.data_ptr(),
+                                            None if intensity is None else intensity.data_ptr(),
+                                            int(line0), int(x.shape[0]), 1 if inverse else 0,
+                                            0.0 if z is None else float(z), self._stream()), "pass_lines")
+        return out
+
+    def pack_transpose(self, x, tile):
+        """(rows, ld) -> (ld // tile, tile, rows): tile c transposed."""
+        rows, ld = x.shape
+        out = self.empty(ld // tile, tile, rows)
+        _lib.check(self.lib.lp2d_pack_transpose(_lib.C64 if self.bits == 64 else _lib.C128, x.data_ptr(), out.data_ptr(),
+                                                rows, ld, tile, self._stream()), "pack_transpose")
+        return out
+
+
+def exchange_transpose(x, backend, group=None):
+    """All-to-all transpose of a slab-decomposed N x N array.
+
+    ``x`` is this rank's ``(N/G, N)`` slab of A (rows ``r*N/G ..``).  Returns this rank's
+    ``(N/G, N)`` slab of A^T.  The same call maps the transposed layout back.
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    nb, n = x.shape
+    if nb * world != n:
+        raise ValueError(f"slab shape {tuple(x.shape)} does not match {world} slabs of an {n} x {n} grid")
+    send = backend.pack_transpose(x, nb)                  # [c][i][k] = x[k][c*nb + i]   (tile c, transposed)
+    if world == 1:
+        recv = send
+    else:
+        recv = send.new_empty(send.shape)
+        dist.all_to_all_single(recv, send, group=group)   # recv[r] = tile (this rank's columns) of rank r's slab, transposed
+    # A^T slab: out[i][r*nb + k] = recv[r][i][k]
+    return recv.permute(1, 0, 2).reshape(nb, n).contiguous() if world > 1 else recv.reshape(nb, n)
+
+
+class SlabBeam2D:
+    """``Beam2D`` semantics (field, spectrum, ``propagate``, ``iprofile``) for ONE grid spread over the
+    ranks of a process group.  ``init_field_gen(X, Y_slab, *args)`` is called with the full 1-D ``X`` and
+    this rank's column vector of ``Y`` (the reference calls generators as ``f(X, Y, *args)``,
+    beam2d.py:119-120), or ``init_field`` gives this rank's ``(N/G, N)`` rows."""
+
+    def __init__(self, area_size, npoints, wl, init_field=None, init_field_gen=None, init_gen_args=(),
+                 complex_bits=64, group=None, backend=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.area_size, self.npoints, self.wl, self.complex_bits = area_size, int(npoints), wl, complex_bits
+        self.z = 0.
+        self.r0, self.r1 = slab_rows(self.npoints, self.rank, self.world)
+        self.backend = backend if backend is not None else CudaLineBackend(area_size, npoints, wl, complex_bits, device)
+        self.dL = area_size / npoints                                       # beam2d.py:299
+        self.X = np.arange(-npoints // 2, npoints // 2, 1) * self.dL        # :300-301
+        self.Y = self.X.reshape((-1, 1))[self.r0:self.r1]                   # this rank's rows of :302
+        self.k0 = 1 / wl
+        npc = np.complex64 if complex_bits == 64 else np.complex128
+        if init_field_gen is not None:
+            f = np.asarray(init_field_gen(self.X.copy(), self.Y.copy(), *init_gen_args)).astype(npc)
+        elif init_field is not None:
+            f = init_field
+        else:
+            raise ValueError("Init field data is None : 'init_field_gen' must be a function or 'init_field' must be an array.")
+        if isinstance(f, np.ndarray):
+            f = torch.from_numpy(np.ascontiguousarray(f.astype(npc)))
+        f = f.to(self.backend.empty(1).device)
+        if tuple(f.shape) != (self.r1 - self.r0, self.npoints):
+            raise ValueError(f"this rank's slab must have shape {(self.r1 - self.r0, self.npoints)}, got {tuple(f.shape)}")
+        self.field = f.contiguous()
+        self.spectrum_t = self._fft2(self.field)
+
+    # forward 2-D transform: field rows -> transposed spectrum columns
+    def _fft2(self, field):
+        rows = self.backend.lines(field, self.r0)                            # FFT along x
+        cols = exchange_transpose(rows, self.backend, self.group)            # this rank's grid columns, as lines
+        return self.backend.lines(cols, self.r0, transposed=True)            # FFT along y
+
+    def propagate(self, z: float, intensity: bool = False):
+        """beam2d.py:481-490 on the decomposed grid; returns this rank's rows of ``|field|^2`` when asked."""
+        if z == 0:
+            return None
+        self.z += z
+        # spectrum *= H (state kept, transposed layout) and inverse transform along y, one local pass
+        cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True, z=z, state_out=self.spectrum_t)
+        rows = exchange_transpose(cols, self.backend, self.group)
+        inten = self.backend.empty(*rows.shape, real=True) if intensity else None
+        self.field = self.backend.lines(rows, self.r0, inverse=True, intensity=inten, out=self.field)
+        return inten
+
+    @property
+    def iprofile(self):
+        """This rank's rows of ``abs(field)**2`` (beam2d.py:717)."""
+        return self.field.real ** 2 + self.field.imag ** 2
+
+    def gather_field(self):
+        """The full N x N field on every rank (debug / small grids)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return self.field
+        parts = [torch.empty_like(self.field) for _ in range(self.world)]
+        dist.all_gather(parts, self.field, group=self.group)
+        return torch.cat(parts, dim=0)
+
+    def gather_spectrum(self):
+        """The full N x N spectrum (natural layout) on every rank (debug / small grids)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return self.spectrum_t.transpose(0, 1).contiguous()
+        parts = [torch.empty_like(self.spectrum_t) for _ in range(self.world)]
+        dist.all_gather(parts, self.spectrum_t, group=self.group)
+        return torch.cat(parts, dim=0).transpose(0, 1).contiguous()

@@ -60,3 +60,105 @@ def test_two_rank_shard_and_gather():
 def test_single_process_gather_is_identity():
     t = torch.arange(6.).reshape(3, 2)
     assert gather_to_rank0(t, 3) is t
+
+
+# --------------------------------------------------------------------------- slab-decomposed grid
+class _NumpyLineBackend:
+    """TEST stand-in for lightprop2d_b200.slab.CudaLineBackend: the same interface, line transforms and
+    the transfer function from the oracle's expressions, CPU torch tensors (so that gloo can move them).
+    Exercises the partitioning / exchange / orientation logic of SlabBeam2D without a GPU."""
+
+    def __init__(self, area_size, npoints, wl, complex_bits):
+        from oracle import beam_oracle as orc
+        self.n = npoints
+        self.g = orc.make_grids(area_size, npoints, wl)
+        self.npc = np.complex64 if complex_bits == 64 else np.complex128
+        self.cdtype = torch.complex64 if complex_bits == 64 else torch.complex128
+        self.rdtype = torch.float32 if complex_bits == 64 else torch.float64
+
+    def empty(self, *shape, real=False):
+        return torch.empty(*shape, dtype=self.rdtype if real else self.cdtype)
+
+    def lines(self, x, line0, inverse=False, transposed=False, z=None, state_out=None, intensity=None, out=None):
+        a = x.numpy().copy()
+        rows = a.shape[0]
+        if z is not None:
+            Kz = self.g["Kz"]                       # [j, i]
+            # slab orientation: natural = rows j of the plane; transposed = line i, position j
+            kz = Kz[:, line0:line0 + rows].T if transposed else Kz[line0:line0 + rows, :]
+            d = kz * z
+            ph = 2 * np.pi * (np.trunc(d) - d)
+            a = (a * (np.cos(ph) + 1j * np.sin(ph))).astype(self.npc)
+            if state_out is not None:
+                state_out.copy_(torch.from_numpy(a))
+        r = (np.fft.ifft(a, axis=-1) if inverse else np.fft.fft(a, axis=-1)).astype(self.npc)
+        res = torch.from_numpy(r)
+        if intensity is not None:
+            intensity.copy_(torch.from_numpy((np.abs(r) ** 2).astype(intensity.numpy().dtype)))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def pack_transpose(self, x, tile):
+        rows, ld = x.shape
+        return x.reshape(rows, ld // tile, tile).permute(1, 2, 0).contiguous()
+
+
+def _slab_worker(rank, world, port, n, bits, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lightprop2d_b200.slab import SlabBeam2D, slab_rows
+        area, wl, z1, z2 = 200e-4 * n / 256, 632e-7, 100e-4, -37e-4
+        rng = np.random.default_rng(5)
+        full = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64 if bits == 64 else np.complex128)
+        r0, r1 = slab_rows(n, rank, world)
+        b = SlabBeam2D(area, n, wl, init_field=full[r0:r1].copy(), complex_bits=bits,
+                       backend=_NumpyLineBackend(area, n, wl, bits))
+        spec0 = b.gather_spectrum().numpy()
+        inten = b.propagate(z1, intensity=True)
+        b.propagate(z2)
+        fld = b.gather_field().numpy()
+        spec = b.gather_spectrum().numpy()
+        if rank == 0:
+            q.put((full, spec0, fld, spec, inten.numpy(), b.z))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slab_matches_oracle():
+    from oracle import beam_oracle as orc
+    world, n, bits = 2, 64, 128
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, bits, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    full, spec0, fld, spec, inten0, z = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    area, wl, z1, z2 = 200e-4 * n / 256, 632e-7, 100e-4, -37e-4
+    o = orc.OracleBeam(area, n, wl, init_field=full.copy(), complex_bits=bits)
+    assert np.linalg.norm(spec0 - o.spectrum) <= 1e-12 * np.linalg.norm(o.spectrum)
+    o.propagate(z1)
+    i1 = o.iprofile[: n // world]
+    assert np.linalg.norm(inten0 - i1) <= 1e-12 * np.linalg.norm(i1)
+    o.propagate(z2)
+    assert abs(z - o.z) < 1e-15
+    assert np.linalg.norm(fld - o.field) <= 1e-12 * np.linalg.norm(o.field)
+    assert np.linalg.norm(spec - o.spectrum) <= 1e-12 * np.linalg.norm(o.spectrum)
+
+
+def test_slab_rows_validation():
+    import pytest
+    from lightprop2d_b200.slab import slab_rows
+    assert slab_rows(1024, 3, 8) == (384, 512)
+    with pytest.raises(ValueError):
+        slab_rows(1000, 0, 3)
+    with pytest.raises(ValueError):
+        slab_rows(1024, 8, 8)

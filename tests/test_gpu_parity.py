@@ -348,3 +348,50 @@ def test_cabi_passes_compose_to_fft2(bits):
     assert lib.lp2d_fft2(plan, x.data_ptr(), t1.data_ptr(), 0, 0, st) == 0         # empty batch
     assert lib.lp2d_propagate(plan, x.data_ptr(), x.data_ptr(), None, B, 1.0, st) == 1
     assert lib.lp2d_pass(plan, _lib.AXIS_ROWS, _lib.OP_FFT_H_IFFT, x.data_ptr(), t1.data_ptr(), None, None, B, 0, 1.0, st) == 2
+
+
+# ----------------------------------------------------------------------------- slab passes (one GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,n", [(64, 256), (64, 1024), (128, 512)])
+def test_slab_single_rank_matches_oracle(bits, n, tol):
+    """SlabBeam2D with one slab = the whole grid: lp2d_pass_lines, the transposed-orientation plan and
+    lp2d_pack_transpose against the oracle (the exchange itself is covered by tests/test_dist_gloo.py
+    and tools/slab_multi_gpu.py)."""
+    from lightprop2d_b200.slab import SlabBeam2D
+    from oracle import beam_oracle as orc
+    rng = np.random.default_rng(n + bits)
+    ct = np.complex64 if bits == 64 else np.complex128
+    f0 = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(ct)
+    area, wl = 200 * lp.um * n / 256, 632 * lp.nm
+    b = SlabBeam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    assert rel_l2(b.gather_spectrum().cpu().numpy(), o.spectrum) <= tol[bits]
+    inten = b.propagate(100 * lp.um, intensity=True)
+    o.propagate(100 * lp.um)
+    assert rel_l2(b.field.cpu().numpy(), o.field) <= tol[bits]
+    assert rel_l2(inten.cpu().numpy(), o.iprofile) <= tol[bits]
+    b.propagate(-40 * lp.um)
+    o.propagate(-40 * lp.um)
+    assert rel_l2(b.field.cpu().numpy(), o.field) <= tol[bits]
+    assert rel_l2(b.gather_spectrum().cpu().numpy(), o.spectrum) <= tol[bits]
+
+
+@pytest.mark.gpu
+def test_pass_lines_partial_slab_equals_full_pass():
+    """Two half-plane slab passes with H (line0 = 0 and n/2) == one whole-plane row pass."""
+    import ctypes as C
+    import torch
+    from lightprop2d_b200 import _lib
+    n = 512
+    f = torch.randn(1, n, n, dtype=torch.complex64, device="cuda")
+    b = lp.Beam2D(200 * lp.um, n, 632 * lp.nm, init_field=f, complex_bits=64, use_gpu=True)
+    lib, plan = _lib.load(), b._plan.handle
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref, out = torch.empty_like(f), torch.empty_like(f)
+    _lib.check(lib.lp2d_pass(plan, _lib.AXIS_ROWS, _lib.OP_H_FFT, f.data_ptr(), ref.data_ptr(), None, None, 1, 1, 0.013, st))
+    half = n // 2 * n * 8
+    for k in range(2):
+        _lib.check(lib.lp2d_pass_lines(plan, _lib.OP_H_FFT, f.data_ptr() + k * half, out.data_ptr() + k * half, None, None,
+                                       k * n // 2, n // 2, 1, 0.013, st))
+    torch.cuda.synchronize()
+    assert torch.equal(ref, out)
