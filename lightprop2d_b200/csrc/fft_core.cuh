@@ -217,8 +217,22 @@ __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sli
         for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
         if (Ns > 1) {
             const int k = j & (Ns - 1);
+            if constexpr (R > 16) {
+                // radix 32: 31 twiddle loads hoisted above their uses would need 62 registers on top of
+                // the 64 of the data (spills at 128 registers): load and apply them eight at a time
 #pragma unroll
-            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+                for (int r0 = 1; r0 < R; r0 += 8) {
+                    cx<T> w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (r0 + i < R) w[i] = __ldg(&tw[twoff + (r0 + i - 1) * Ns + k]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (r0 + i < R) u[r0 + i] = cmul(u[r0 + i], w[i]);
+                    asm volatile("" ::: "memory");
+                }
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+            }
         }
         dft_reg<T, R>(u);
         if (last) {

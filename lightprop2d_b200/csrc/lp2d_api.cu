@@ -8,7 +8,6 @@
 
 #include "../../include/lp2d.h"
 #include "dispatch.h"
-#include "pipe_ops.cuh"
 #include "pipe2_ops.cuh"
 
 namespace lp2d {
@@ -53,17 +52,12 @@ struct lp2d_plan {
     cudaStream_t aux[8];
     cudaEvent_t ev_fork;
     cudaEvent_t ev_join[8];
-    // persistent pipeline kernel (pipeline.cuh): one launch per 2-D step
-    const PipeOps<float>* pipe32;
-    const PipeOps<double>* pipe64;
-    int pipe_ctas_factor, pipe_ctas_plain;   // resident CTAs per SM with / without the factor table
     int num_sms;
     void* ring;                // L2-resident intermediate planes
     long long ring_bytes;
     unsigned int* counters;    // work queue head + per-(stage, group) completion counters
     int counters_cap;
     int pipe_g, pipe_lag, pipe_slots, pipe_grid;   // tuning overrides (0 = automatic)
-    int pipe_mode;             // 0: persistent CTAs, 1: one CTA per item (ticket)
     int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
     int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
     int fused_ops;             // which steps use the fused step kernel: 1 plain fft2, 2 steps that store state
@@ -182,43 +176,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         cudaFree(p->tw); cudaFree(p->tabs); delete p;
         return cuda_fail(e, "cudaMemcpy(tables)");
     }
-    // persistent pipeline: available when the kernel exists for (n, dtype) and two planes fit the ring
-    p->pipe32 = nullptr; p->pipe64 = nullptr; p->ring = nullptr; p->counters = nullptr;
-    p->ring_bytes = 0; p->counters_cap = 0;
-    // opt-in (LP2D_PIPE=1): it moves only the algorithmic bytes through HBM but is, in this round,
-    // not yet faster than the one-kernel-per-pass path ("The persistent pipeline kernel")
-    env = getenv("LP2D_PIPE");
-    if (env != nullptr && atoi(env) == 1) {
-        env = getenv("LP2D_PIPE_VARIANT");
-        const int pvar = env ? atoi(env) : 0;
-        const PipeOps<float>* q32 = dtype == LP2D_C64 ? find_pipe_f32(n, pvar) : nullptr;
-        const PipeOps<double>* q64 = dtype == LP2D_C128 ? find_pipe_f64(n, pvar) : nullptr;
-        // the pipeline shares the twiddle table of the line kernels: same (N, E) schedule required
-        if (q32 && q32->e != o32->e) q32 = nullptr;
-        if (q64 && q64->e != o64->e) q64 = nullptr;
-        env = getenv("LP2D_RING_MB");
-        const long long ring_bytes = (env ? atoll(env) : 96) * (1ll << 20);
-        const long long plane = (long long)n * n * (dtype == LP2D_C64 ? 8 : 16);
-        if ((q32 || q64) && 2 * plane <= ring_bytes) {
-            env = getenv("LP2D_PIPE_MODE");
-            p->pipe_mode = env ? atoi(env) : 1;
-            if (p->pipe_mode == 1)
-                e = q32 ? q32->configure_ticket(&p->pipe_ctas_factor, &p->pipe_ctas_plain)
-                        : q64->configure_ticket(&p->pipe_ctas_factor, &p->pipe_ctas_plain);
-            else
-                e = q32 ? q32->configure(&p->pipe_ctas_factor, &p->pipe_ctas_plain)
-                        : q64->configure(&p->pipe_ctas_factor, &p->pipe_ctas_plain);
-            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
-            p->counters_cap = 1 + PIPE_MAX_STAGES * 16384;
-            if (e == cudaSuccess) e = cudaMalloc(&p->ring, (size_t)ring_bytes);
-            if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * p->counters_cap);
-            if (e != cudaSuccess || p->pipe_ctas_factor < 1 || p->pipe_ctas_plain < 1) {
-                cudaFree(p->ring); cudaFree(p->counters); cudaFree(p->tw); cudaFree(p->tabs); delete p;
-                return e != cudaSuccess ? cuda_fail(e, "pipeline setup") : fail(LP2D_ECUDA, "pipeline kernel does not fit an SM");
-            }
-            p->pipe32 = q32; p->pipe64 = q64; p->ring_bytes = ring_bytes;
-        }
-    }
+    p->ring = nullptr; p->counters = nullptr; p->ring_bytes = 0; p->counters_cap = 0; p->num_sms = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -236,7 +194,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             const size_t n2 = w2.size() / 2;
             e = q32 ? q32->configure(&p->p2_ctas_factor, &p->p2_ctas_plain) : q64->configure(&p->p2_ctas_factor, &p->p2_ctas_plain);
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
-            p->counters_cap = 1 + PIPE_MAX_STAGES * 16384;
+            p->counters_cap = 1 + P2_MAX_STAGES * 16384;
             if (e == cudaSuccess) e = cudaMalloc(&p->ring, (size_t)ring_bytes);
             if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * p->counters_cap);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_tw, n2 * csz);
@@ -326,19 +284,6 @@ namespace {
 template <typename T> const SizeOps<T>* ops_of(const lp2d_plan* p);
 template <> const SizeOps<float>* ops_of<float>(const lp2d_plan* p) { return p->ops32; }
 template <> const SizeOps<double>* ops_of<double>(const lp2d_plan* p) { return p->ops64; }
-
-template <typename T> const PipeOps<T>* pipe_of(const lp2d_plan* p);
-template <> const PipeOps<float>* pipe_of<float>(const lp2d_plan* p) { return p->pipe32; }
-template <> const PipeOps<double>* pipe_of<double>(const lp2d_plan* p) { return p->pipe64; }
-
-template <typename T>
-StageArgs<T> stage(int axis, int inverse, T scale) {
-    StageArgs<T> st;
-    memset(&st, 0, sizeof st);
-    st.axis = axis; st.inverse = inverse; st.scale = scale;
-    return st;
-}
-
 
 template <typename T> const P2Ops<T>* p2_of(const lp2d_plan* p);
 template <> const P2Ops<float>* p2_of<float>(const lp2d_plan* p) { return p->p2_32; }
@@ -439,78 +384,6 @@ P2Stage<T> p2_stage(int axis, int inverse, T scale) {
     return st;
 }
 
-// Run a chain of `nstages` line passes over `batch` beams in one persistent launch (pipeline.cuh).
-// Returns -1 when the pipeline is not available for this plan / step (the caller then uses the
-// one-kernel-per-pass path), otherwise an LP2D status.
-template <typename T>
-int run_pipeline(const lp2d_plan* p, const StageArgs<T>* stages, int nstages, bool need_factor, long long batch,
-                 double z, double lens_k0, double lens_2f, cudaStream_t s) {
-    const PipeOps<T>* ops = pipe_of<T>(p);
-    if (ops == nullptr) return -1;
-    const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
-    const int ctas = need_factor ? p->pipe_ctas_factor : p->pipe_ctas_plain;
-    long long conc = (long long)ctas * p->num_sms;
-    if (p->pipe_grid > 0 && p->pipe_grid < conc) conc = p->pipe_grid;
-    const int tiles = ops->tiles;
-    // lag (in groups) between consecutive stages of one group: the items in between cover all resident CTAs
-    // (twice: the dependencies of an item are looked at one item ahead of its start)
-    const long long reach = (p->pipe_mode == 1) ? (5 * conc) / 4 : 2 * conc;
-    int lag = p->pipe_lag > 0 ? p->pipe_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles));
-    if (lag < 1) lag = 1;
-    // ring slots (groups): a power of two (the kernel masks), at least one more than the number of
-    // groups between the first and the last stage
-    const int slots_need = (nstages - 1) * lag + 1;
-    int slots_min = 2;
-    while (slots_min < slots_need) slots_min *= 2;
-    int slots = slots_min;
-    if (p->pipe_slots > 0) { slots = 2; while (slots < p->pipe_slots) slots *= 2; if (slots < slots_min) slots = slots_min; }
-    // beams per group: amortise the FP64 factor table, bounded by the ring
-    long long G = p->pipe_g > 0 ? p->pipe_g : (need_factor ? 4 : 1);
-    if (G > batch) G = batch;
-    while (G > 1 && slots * G * plane > p->ring_bytes) --G;
-    if (slots * G * plane > p->ring_bytes) return -1;
-    if (p->pipe_slots == 0 && 2 * slots * G * plane <= p->ring_bytes && slots == slots_need) slots *= 2;   // slack
-
-    const long long groups_cap = (p->counters_cap - 1) / nstages;
-    for (long long b0 = 0; b0 < batch; b0 += groups_cap * G) {
-        const long long nb = (batch - b0 < groups_cap * G) ? batch - b0 : groups_cap * G;
-        PipeArgs<T> a;
-        memset(&a, 0, sizeof a);
-        const long long off = b0 * (long long)p->n * p->n;
-        for (int i = 0; i < nstages; ++i) {
-            a.st[i] = stages[i];
-            StageArgs<T>& st = a.st[i];
-            if (st.in) st.in += off;
-            if (st.out) st.out += off;
-            if (st.out_pre) st.out_pre += off;
-            if (st.out_mid) st.out_mid += off;
-            if (st.inten) st.inten += off;
-            if (st.mask) st.mask = static_cast<const char*>(st.mask) + b0 * st.mask_beam_stride *
-                                   (st.mask_kind == MASK_CX ? sizeof(cx<T>) : st.mask_kind == MASK_REAL ? sizeof(T) : 1);
-        }
-        a.ring = static_cast<cx<T>*>(p->ring);
-        a.tw = static_cast<const cx<T>*>(p->tw);
-        a.a_tab = p->tabs; a.b_tab = p->tabs + p->n; a.x2_tab = p->tabs + 2 * p->n;
-        a.counters = p->counters;
-        a.z = z; a.lens_k0 = lens_k0; a.lens_2f = lens_2f;
-        a.nbeams = nb;
-        a.nstages = nstages;
-        a.ngroups = (int)((nb + G - 1) / G);
-        a.G = (int)G; a.lag = lag; a.ring_slots = slots;
-        const long long total = ((long long)a.ngroups + (long long)(nstages - 1) * lag) * nstages * tiles;
-        if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "pipeline: batch too large for one launch");
-        a.total_items = (int)total;
-        LP2D_CU(cudaMemsetAsync(p->counters, 0, sizeof(unsigned int) * (1 + (size_t)nstages * a.ngroups), s), "pipeline counters");
-        if (p->pipe_mode == 1) {
-            LP2D_CU(ops->launch_ticket(a, (unsigned)total, need_factor, s), "pipeline launch");
-        } else {
-            const unsigned grid = (unsigned)(total < conc ? total : conc);
-            LP2D_CU(ops->launch(a, grid, need_factor, s), "pipeline launch");
-        }
-    }
-    return LP2D_OK;
-}
-
 template <typename T>
 LineArgs<T> base_args(const lp2d_plan* p) {
     LineArgs<T> a;
@@ -604,18 +477,6 @@ int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const v
         const int rc = (p->fused_ops & (state_out != nullptr ? 2 : 1)) ? run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s) : -1;
         if (rc >= 0) return rc;
     }
-    {
-        StageArgs<T> st[2] = {stage<T>(AX_ROW, inverse, sc), stage<T>(AX_COL, inverse, sc)};
-        st[0].in = static_cast<const cx<T>*>(in);
-        st[0].out_pre = static_cast<cx<T>*>(state_out);
-        st[0].out_ring = 1;
-        st[0].pre = (pre == PRE_LENS) ? FAC_LENS : FAC_NONE;
-        if (mask != nullptr) { st[0].mask = mask; st[0].mask_kind = mask_kind; st[0].mask_beam_stride = mask_stride; }
-        st[1].in_ring = 1;
-        st[1].out = static_cast<cx<T>*>(other);
-        const int rc = run_pipeline<T>(p, st, 2, pre == PRE_LENS, batch, 0.0, k0, two_f, s);
-        if (rc >= 0) return rc;
-    }
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
     const int H = p->hints;
@@ -666,18 +527,6 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         const int rc = (p->fused_ops & 2) ? run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s) : -1;
         if (rc >= 0) return rc;
     }
-    {
-        StageArgs<T> st[2] = {stage<T>(AX_ROW, 1, sc), stage<T>(AX_COL, 1, sc)};
-        st[0].in = static_cast<const cx<T>*>(spectrum);
-        st[0].out_pre = static_cast<cx<T>*>(spectrum);
-        st[0].pre = FAC_H;
-        st[0].out_ring = 1;
-        st[1].in_ring = 1;
-        st[1].out = static_cast<cx<T>*>(field);
-        st[1].inten = static_cast<T*>(intensity);
-        const int rc = run_pipeline<T>(p, st, 2, true, batch, z, 0.0, 0.0, s);
-        if (rc >= 0) return rc;
-    }
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
     const int H = p->hints;
@@ -721,19 +570,6 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
         st[2].out = static_cast<cx<T>*>(fout);
         st[2].inten = static_cast<T*>(intensity);
         const int rc = (p->fused_ops & 4) ? run_p2<T>(p, st, 3, P2_FAC_H, 1, z, 0.0, batch, s) : -1;
-        if (rc >= 0) return rc;
-    }
-    {
-        const T inv_n = (T)(1.0 / (double)p->n);
-        StageArgs<T> st[3] = {stage<T>(AX_ROW, 0, (T)1), stage<T>(AX_COL, 0, inv_n), stage<T>(AX_ROW, 1, inv_n)};
-        st[0].in = static_cast<const cx<T>*>(fin);
-        st[0].out_ring = 1;
-        st[1].in_ring = 1; st[1].out_ring = 1; st[1].mid = 1;
-        st[1].out_mid = static_cast<cx<T>*>(spec_out);
-        st[2].in_ring = 1;
-        st[2].out = static_cast<cx<T>*>(fout);
-        st[2].inten = static_cast<T*>(intensity);
-        const int rc = run_pipeline<T>(p, st, 3, true, batch, z, 0.0, 0.0, s);
         if (rc >= 0) return rc;
     }
     const long long plane = (long long)p->n * p->n;

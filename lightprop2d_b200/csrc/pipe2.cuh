@@ -647,8 +647,16 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
                 for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
             }
             if (use_pre) {
+                // eight factors at a time (32 loads in flight would double the register footprint)
 #pragma unroll
-                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]));
+                for (int m0 = 0; m0 < E; m0 += 8) {
+                    cx<T> h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (m0 + i < E) h[i] = __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * (m0 + i), m0 + i)]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (m0 + i < E) v[m0 + i] = cmul(v[m0 + i], h[i]);
+                    if (E > 16) asm volatile("" ::: "memory");
+                }
             }
             if (st.out_pre != nullptr) {
                 cx<T>* dst = st.out_pre + b * PLANE + off0 + t * PSTRIDE;
