@@ -1,6 +1,7 @@
 // Pointwise / resampling / reduction kernels around the transform passes:
 // expand (edge-replicating pad), coarse (block mean), phase, intensity moments,
 // and the SIMT form of the mode projection / synthesis.
+#include <cstdlib>
 #include <string>
 
 #include "../../include/lp2d.h"
@@ -8,6 +9,8 @@
 
 namespace lp2d {
 int set_error(int code, const std::string& msg);   // lp2d_api.cu
+int modes_project_tc(const void* field, const void* modes, void* coeffs, int n, int nb, int nmodes, long long batch,
+                     cudaStream_t s);              // lp2d_modes_tc.cu
 
 // out[b][r][c] = in[b][clamp(r-pad)][clamp(c-pad)]      (beam2d.py:392-401)
 template <typename T>
@@ -272,6 +275,14 @@ int lp2d_modes_project(int dtype, const void* field, const void* modes, void* co
         return set_error(LP2D_EINVAL, "modes_project: bad arguments");
     if (batch == 0) return LP2D_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == LP2D_C64) {
+        // tensor-core form (tcgen05, 3xTF32) for complex64 when the crop rows are a multiple of the K block
+        const char* env = getenv("LP2D_MODES_TC");
+        if (env == nullptr || atoi(env) != 0) {
+            const int rc = modes_project_tc(field, modes, coeffs, n, nb, nmodes, batch, s);
+            if (rc != LP2D_EUNSUPPORTED) return rc;
+        }
+    }
     dim3 grid((unsigned)nmodes, (unsigned)batch);
     if (dtype == LP2D_C64)
         modes_project_kernel<float><<<grid, 256, 0, s>>>((const float2*)field, (const float2*)modes, (float2*)coeffs, n, nb, nmodes);

@@ -1,0 +1,308 @@
+// Mode projection on the 5th-generation tensor cores (tcgen05, accumulators in TMEM).
+//
+//   coeffs[b][m] = sum_p modes[m][p] * field_b[crop(p)]        (no conjugate, beam2d.py:592-600)
+//
+// is a complex GEMM with a tiny output (batch x nmodes) and a huge reduction (p = nb^2 samples of the
+// centred crop).  It is mapped on ONE real TF32 GEMM per CTA tile:
+//
+//   A (UMMA M = 128 rows)   = 128 modes, as stored: (Mr, Mi) interleaved along K (K-major)
+//   B (UMMA N = 2 * 64 rows) = for every beam the two rows (Fr, -Fi) and (Fi, Fr), so that
+//   D[m][2b]   = sum Mr*Fr - Mi*Fi = Re coeffs[b][m],     D[m][2b+1] = sum Mr*Fi + Mi*Fr = Im coeffs[b][m]
+//
+// FP32 accuracy out of TF32 products (the parity bound is 1e-5): every operand is split as
+// x = hi + lo with hi = x rounded to TF32 and lo = x - hi (exact in FP32), and the three products
+// hi*hi + hi*lo + lo*hi are accumulated (3xTF32; lo*lo is below 2^-22 relative).
+//
+// The reduction is split over the CTAs (split-K): a CTA owns a contiguous range of K blocks and
+// accumulates them in TMEM (128 lanes x 128 FP32 columns).  The tensor core truncates when it adds to
+// the accumulator, so the error of one accumulation chain grows linearly with its length (measured:
+// 2.5e-5 relative after 55 blocks): every FLUSH blocks the chain is read back (tcgen05.ld) and added
+// -- round to nearest -- to FP32 registers, and the next MMA starts a fresh chain; at the end the
+// register sums are added to the zero-initialised output with FP32 atomics (red.global.add.f32).
+//
+// Per K block (32 complex samples = 64 TF32 values per row = 8 MMA K-steps): the 256 threads copy the
+// mode tile and the field tile from HBM (coalesced 16-byte loads, issued one block ahead so that they
+// overlap the MMAs), split / combine them in registers, and write the four operand tiles to shared
+// memory in the canonical no-swizzle K-major UMMA layout ([16-byte K chunk][row], chunk stride padded
+// by 16 bytes against bank conflicts); one thread issues the 24 tcgen05.mma and commits them to an
+// mbarrier that the next overwrite of the tiles waits on.
+#include <cstdint>
+#include <string>
+
+#include "../../include/lp2d.h"
+#include <cuda_runtime.h>
+
+namespace lp2d {
+int set_error(int code, const std::string& msg);   // lp2d_api.cu
+extern long long g_launches;
+
+namespace tc {
+
+constexpr int UM = 128;            // modes per tile (UMMA M)
+constexpr int BT = 64;             // beams per tile
+constexpr int UN = 2 * BT;         // UMMA N
+constexpr int KB = 32;             // complex samples per K block
+constexpr int CHUNKS = KB / 2;     // 16-byte K chunks per row and block (4 TF32 values = 2 complex samples)
+constexpr int THREADS = 256;
+constexpr int FLUSH = 4;            // K blocks per TMEM accumulation chain
+constexpr int ACC = UN / 2;         // accumulator columns per thread: warp w owns lanes 32*(w%4).., columns ACC*(w/4)..
+constexpr int CH_A = UM * 16 + 16; // byte stride between K chunks of the A tiles (padded)
+constexpr int CH_B = UN * 16 + 16;
+constexpr int TILE_A = CHUNKS * CH_A;
+constexpr int TILE_B = CHUNKS * CH_B;
+constexpr int SMEM_BYTES = 2 * TILE_A + 2 * TILE_B + 1024;
+constexpr int A_LD = UM * CHUNKS / THREADS;        // 16-byte loads per thread and block: modes
+constexpr int B_LD = BT * CHUNKS / THREADS;        // ... fields
+constexpr int TMEM_COLS = 128;                     // FP32 accumulator columns (= UN)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address [0,14), leading byte offset [16,30) = distance between the two 16-byte K chunks of one
+// MMA, stride byte offset [32,46) = distance between 8-row groups, version [46,48) = 1, layout type
+// [61,64) = 0; all offsets in units of 16 bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A = B = TF32 [7,10), [10,13) = 2,
+// both K-major (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = clock64();
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();      // never hang the device on a lost arrive
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// x = hi + lo, hi = x rounded to nearest TF32 (10 explicit mantissa bits), lo = x - hi exactly
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+struct Args {
+    const float2* field;    // batch x n x n
+    const float2* modes;    // nmodes x nb*nb
+    float* coeffs;          // batch x nmodes complex, zero-initialised; partial sums are added
+    int n, nb, nmodes, batch;
+    int kblocks;            // nb*nb / KB
+    int ksplit;             // CTAs along the reduction
+    int mtiles, btiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = a_hi + TILE_A;
+    unsigned char* b_hi = a_lo + TILE_A;
+    unsigned char* b_lo = b_hi + TILE_B;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    const int tile = blockIdx.x / p.ksplit, ks = blockIdx.x % p.ksplit;
+    const int mt = tile % p.mtiles, bt = tile / p.mtiles;
+    const int m0 = mt * UM, b0 = bt * BT;
+    const int kb_lo = (int)((long long)p.kblocks * ks / p.ksplit), kb_hi = (int)((long long)p.kblocks * (ks + 1) / p.ksplit);
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    const int dn = (p.n - p.nb) / 2;
+    const long long kk = (long long)p.nb * p.nb;
+    // per-thread load assignment: piece q = tid + THREADS*i -> (row, chunk) = (q / CHUNKS, q % CHUNKS):
+    // 16 consecutive threads read the 256 contiguous bytes of one row of the block
+    float4 ra[A_LD], rb[B_LD];
+    auto load_block = [&](int kb) {
+        const long long p0 = (long long)kb * KB;                 // first crop sample of the block
+        const int cy = (int)(p0 / p.nb), cx0 = (int)(p0 % p.nb); // KB divides nb: a block stays in one crop row
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
+            ra[i] = (m0 + row < p.nmodes) ? __ldcs(reinterpret_cast<const float4*>(p.modes + (long long)(m0 + row) * kk + p0) + c)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
+            rb[i] = (b0 + row < p.batch)
+                        ? __ldg(reinterpret_cast<const float4*>(p.field + ((long long)(b0 + row) * p.n + dn + cy) * p.n + dn + cx0) + c)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_block = [&]() {
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
+            float4 h, l;
+            split_tf32(ra[i].x, h.x, l.x); split_tf32(ra[i].y, h.y, l.y);
+            split_tf32(ra[i].z, h.z, l.z); split_tf32(ra[i].w, h.w, l.w);
+            *reinterpret_cast<float4*>(a_hi + c * CH_A + row * 16) = h;
+            *reinterpret_cast<float4*>(a_lo + c * CH_A + row * 16) = l;
+        }
+#pragma unroll
+        for (int i = 0; i < B_LD; ++i) {
+            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
+            // two complex samples (x, y), (z, w) of beam `row`: row 2b = (Fr, -Fi), row 2b+1 = (Fi, Fr)
+            const float4 f = rb[i];
+            const float4 re = make_float4(f.x, -f.y, f.z, -f.w), im = make_float4(f.y, f.x, f.w, f.z);
+            float4 h, l;
+            split_tf32(re.x, h.x, l.x); split_tf32(re.y, h.y, l.y); split_tf32(re.z, h.z, l.z); split_tf32(re.w, h.w, l.w);
+            *reinterpret_cast<float4*>(b_hi + c * CH_B + (2 * row) * 16) = h;
+            *reinterpret_cast<float4*>(b_lo + c * CH_B + (2 * row) * 16) = l;
+            split_tf32(im.x, h.x, l.x); split_tf32(im.y, h.y, l.y); split_tf32(im.z, h.z, l.z); split_tf32(im.w, h.w, l.w);
+            *reinterpret_cast<float4*>(b_hi + c * CH_B + (2 * row + 1) * 16) = h;
+            *reinterpret_cast<float4*>(b_lo + c * CH_B + (2 * row + 1) * 16) = l;
+        }
+    };
+
+    // this thread's part of the accumulator: TMEM lane 32*(warp%4) + lane-in-warp, columns col0 .. col0+ACC-1
+    float acc[ACC];
+#pragma unroll
+    for (int j = 0; j < ACC; ++j) acc[j] = 0.f;
+    const int col0 = (warp >> 2) * ACC;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+    auto flush = [&]() {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < ACC; c0 += 16) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(tlane + (uint32_t)c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    uint32_t parity = 0;
+    if (kb_lo < kb_hi) load_block(kb_lo);
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const bool fresh = ((kb - kb_lo) % FLUSH) == 0;          // this block starts a new accumulation chain
+        if (kb > kb_lo) {                       // the MMAs of the previous block have read the tiles
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
+            if (fresh) flush();                 // ... and the chain they closed is complete
+        }
+        store_block();
+        if (kb + 1 < kb_hi) load_block(kb + 1); // in flight while the tensor core works on this block
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+#pragma unroll
+            for (int s = 0; s < CHUNKS / 2; ++s) {              // one MMA K-step = 8 TF32 values = 2 chunks
+                const uint64_t dah = umma_desc(sa_hi + 2 * s * CH_A, CH_A, 128), dal = umma_desc(sa_lo + 2 * s * CH_A, CH_A, 128);
+                const uint64_t dbh = umma_desc(sb_hi + 2 * s * CH_B, CH_B, 128), dbl = umma_desc(sb_lo + 2 * s * CH_B, CH_B, 128);
+                mma_tf32(tmem, dah, dbh, (!fresh || s > 0) ? 1u : 0u);
+                mma_tf32(tmem, dah, dbl, 1u);
+                mma_tf32(tmem, dal, dbh, 1u);
+            }
+            umma_commit(&s_bar);                                // arrives when the MMAs above are complete
+        }
+    }
+    if (kb_lo < kb_hi) {
+        mbar_wait(&s_bar, parity);
+        flush();
+        // epilogue: lane = mode m0 + 32*(warp%4) + lane-in-warp, column c = (beam, re/im)
+        const int m = m0 + (warp & 3) * 32 + (tid & 31);
+        if (m < p.nmodes) {
+#pragma unroll
+            for (int j = 0; j < ACC; ++j) {
+                const int col = col0 + j, b = b0 + (col >> 1);
+                if (b < p.batch) atomicAdd(p.coeffs + ((long long)b * p.nmodes + m) * 2 + (col & 1), acc[j]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tc
+
+// complex64 only; nb must be a multiple of the K block.  Returns LP2D_EUNSUPPORTED when the shape
+// is not covered (the caller then uses the SIMT kernel).
+int modes_project_tc(const void* field, const void* modes, void* coeffs, int n, int nb, int nmodes, long long batch,
+                     cudaStream_t s) {
+    using namespace tc;
+    if (nb % KB != 0 || ((n - nb) / 2) % 2 != 0 || n % 2 != 0) return LP2D_EUNSUPPORTED;   // 16-byte aligned rows
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(modes_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project_tc setup: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    Args a;
+    a.field = static_cast<const float2*>(field);
+    a.modes = static_cast<const float2*>(modes);
+    a.coeffs = static_cast<float*>(coeffs);
+    a.n = n; a.nb = nb; a.nmodes = nmodes; a.batch = (int)batch;
+    a.kblocks = (int)((long long)nb * nb / KB);
+    a.mtiles = (nmodes + UM - 1) / UM;
+    a.btiles = (int)((batch + BT - 1) / BT);
+    const int tiles = a.mtiles * a.btiles;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int ksplit = (2 * sms + tiles - 1) / tiles;            // about two waves of CTAs (one CTA per SM at a time)
+    if (ksplit > a.kblocks) ksplit = a.kblocks;
+    if (ksplit < 1) ksplit = 1;
+    a.ksplit = ksplit;
+    cudaError_t e = cudaMemsetAsync(coeffs, 0, sizeof(float2) * (size_t)batch * nmodes, s);
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project_tc memset: ") + cudaGetErrorString(e));
+    modes_project_tc_kernel<<<(unsigned)(tiles * ksplit), THREADS, SMEM_BYTES, s>>>(a);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project_tc launch: ") + cudaGetErrorString(e));
+    return LP2D_OK;
+}
+
+}  // namespace lp2d
