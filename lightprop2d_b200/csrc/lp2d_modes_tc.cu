@@ -20,14 +20,16 @@
 // -- round to nearest -- to FP32 registers, and the next MMA starts a fresh chain; at the end the
 // register sums are added to the zero-initialised output with FP32 atomics (red.global.add.f32).
 //
-// Per K block (32 complex samples = 64 TF32 values per row = 8 MMA K-steps): the 256 threads copy the
-// mode tile and the field tile from HBM (coalesced 16-byte loads, issued one block ahead so that they
-// overlap the MMAs), split / combine them in registers, and write the four operand tiles to shared
-// memory in the canonical no-swizzle K-major UMMA layout ([16-byte K chunk][row], chunk stride padded
-// by 16 bytes against bank conflicts); one thread issues the 24 tcgen05.mma and commits them to an
-// mbarrier that the next overwrite of the tiles waits on.
+// Per K block (16 complex samples = 32 TF32 values per row = 4 MMA K-steps): the 256 threads copy the
+// mode tile and the field tile from HBM (coalesced 16-byte loads, issued one block ahead), split /
+// combine them in registers, and write the four operand tiles to one of two shared-memory stages in
+// the canonical no-swizzle K-major UMMA layout ([16-byte K chunk][row], chunk stride padded by 16
+// bytes against bank conflicts); one thread issues the 12 tcgen05.mma of the block and commits them
+// to the stage's mbarrier, which the next overwrite of that stage waits on -- so the tensor core
+// works on block k while the threads stage block k+1.
 #include <cstdint>
 #include <string>
+#include <type_traits>
 
 #include "../../include/lp2d.h"
 #include <cuda_runtime.h>
@@ -41,16 +43,19 @@ namespace tc {
 constexpr int UM = 128;            // modes per tile (UMMA M)
 constexpr int BT = 64;             // beams per tile
 constexpr int UN = 2 * BT;         // UMMA N
-constexpr int KB = 32;             // complex samples per K block
+constexpr int KB = 16;             // complex samples per K block
 constexpr int CHUNKS = KB / 2;     // 16-byte K chunks per row and block (4 TF32 values = 2 complex samples)
 constexpr int THREADS = 256;
-constexpr int FLUSH = 4;            // K blocks per TMEM accumulation chain
+constexpr int FLUSH = 8;            // K blocks per TMEM accumulation chain
+constexpr int PF = 3;               // K blocks of global loads in flight per thread (register sets)
+constexpr int STAGES = 2;           // operand tile sets in shared memory (the stores of block k+1 overlap the MMAs of block k)
 constexpr int ACC = UN / 2;         // accumulator columns per thread: warp w owns lanes 32*(w%4).., columns ACC*(w/4)..
 constexpr int CH_A = UM * 16 + 16; // byte stride between K chunks of the A tiles (padded)
 constexpr int CH_B = UN * 16 + 16;
 constexpr int TILE_A = CHUNKS * CH_A;
 constexpr int TILE_B = CHUNKS * CH_B;
-constexpr int SMEM_BYTES = 2 * TILE_A + 2 * TILE_B + 1024;
+constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
 constexpr int A_LD = UM * CHUNKS / THREADS;        // 16-byte loads per thread and block: modes
 constexpr int B_LD = BT * CHUNKS / THREADS;        // ... fields
 constexpr int TMEM_COLS = 128;                     // FP32 accumulator columns (= UN)
@@ -120,12 +125,8 @@ struct Args {
 
 __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t s_bar;
+    __shared__ uint64_t s_bar[STAGES];
     __shared__ uint32_t s_tmem;
-    unsigned char* a_hi = smem;
-    unsigned char* a_lo = a_hi + TILE_A;
-    unsigned char* b_hi = a_lo + TILE_A;
-    unsigned char* b_lo = b_hi + TILE_B;
     const int tid = threadIdx.x, warp = tid >> 5;
 
     const int tile = blockIdx.x / p.ksplit, ks = blockIdx.x % p.ksplit;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
     const int kb_lo = (int)((long long)p.kblocks * ks / p.ksplit), kb_hi = (int)((long long)p.kblocks * (ks + 1) / p.ksplit);
 
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+        for (int i = 0; i < STAGES; ++i) mbar_init(&s_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -150,31 +151,37 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
     const long long kk = (long long)p.nb * p.nb;
     // per-thread load assignment: piece q = tid + THREADS*i -> (row, chunk) = (q / CHUNKS, q % CHUNKS):
     // 16 consecutive threads read the 256 contiguous bytes of one row of the block
-    float4 ra[A_LD], rb[B_LD];
-    auto load_block = [&](int kb) {
+    float4 ra[PF][A_LD], rb[PF][B_LD];
+    auto load_block = [&](int kb, auto set_c) {
+        constexpr int SET = decltype(set_c)::value;
         const long long p0 = (long long)kb * KB;                 // first crop sample of the block
         const int cy = (int)(p0 / p.nb), cx0 = (int)(p0 % p.nb); // KB divides nb: a block stays in one crop row
 #pragma unroll
         for (int i = 0; i < A_LD; ++i) {
             const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
-            ra[i] = (m0 + row < p.nmodes) ? __ldcs(reinterpret_cast<const float4*>(p.modes + (long long)(m0 + row) * kk + p0) + c)
+            ra[SET][i] = (m0 + row < p.nmodes) ? __ldcs(reinterpret_cast<const float4*>(p.modes + (long long)(m0 + row) * kk + p0) + c)
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < B_LD; ++i) {
             const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
-            rb[i] = (b0 + row < p.batch)
+            rb[SET][i] = (b0 + row < p.batch)
                         ? __ldg(reinterpret_cast<const float4*>(p.field + ((long long)(b0 + row) * p.n + dn + cy) * p.n + dn + cx0) + c)
                         : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    auto store_block = [&]() {
+    auto store_block = [&](int stage, auto set_c) {
+        constexpr int SET = decltype(set_c)::value;
+        unsigned char* a_hi = smem + stage * STAGE_BYTES;
+        unsigned char* a_lo = a_hi + TILE_A;
+        unsigned char* b_hi = a_lo + TILE_A;
+        unsigned char* b_lo = b_hi + TILE_B;
 #pragma unroll
         for (int i = 0; i < A_LD; ++i) {
             const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
             float4 h, l;
-            split_tf32(ra[i].x, h.x, l.x); split_tf32(ra[i].y, h.y, l.y);
-            split_tf32(ra[i].z, h.z, l.z); split_tf32(ra[i].w, h.w, l.w);
+            split_tf32(ra[SET][i].x, h.x, l.x); split_tf32(ra[SET][i].y, h.y, l.y);
+            split_tf32(ra[SET][i].z, h.z, l.z); split_tf32(ra[SET][i].w, h.w, l.w);
             *reinterpret_cast<float4*>(a_hi + c * CH_A + row * 16) = h;
             *reinterpret_cast<float4*>(a_lo + c * CH_A + row * 16) = l;
         }
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
         for (int i = 0; i < B_LD; ++i) {
             const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
             // two complex samples (x, y), (z, w) of beam `row`: row 2b = (Fr, -Fi), row 2b+1 = (Fi, Fr)
-            const float4 f = rb[i];
+            const float4 f = rb[SET][i];
             const float4 re = make_float4(f.x, -f.y, f.z, -f.w), im = make_float4(f.y, f.x, f.w, f.z);
             float4 h, l;
             split_tf32(re.x, h.x, l.x); split_tf32(re.y, h.y, l.y); split_tf32(re.z, h.z, l.z); split_tf32(re.w, h.w, l.w);
@@ -218,23 +225,31 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    uint32_t parity = 0;
-    if (kb_lo < kb_hi) load_block(kb_lo);
-    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+    // commits issued so far on each stage's mbarrier; the latest one is phase uses - 1
+    int uses[STAGES];
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) uses[i] = 0;
+    auto wait_stage = [&](int stage) {
+        if (uses[stage] > 0) mbar_wait(&s_bar[stage], (uint32_t)((uses[stage] - 1) & 1));
+    };
+    // one K block: stage the register set SET (loaded PF blocks ago), refill it, multiply
+    auto step = [&](int kb, auto set_c) {
+        const int stage = (kb - kb_lo) % STAGES;
         const bool fresh = ((kb - kb_lo) % FLUSH) == 0;          // this block starts a new accumulation chain
-        if (kb > kb_lo) {                       // the MMAs of the previous block have read the tiles
-            mbar_wait(&s_bar, parity);
-            parity ^= 1;
-            if (fresh) flush();                 // ... and the chain they closed is complete
+        if (fresh && kb > kb_lo) {
+            // the chain closed by the previous block is complete (a commit covers every earlier MMA)
+            wait_stage((kb - 1 - kb_lo) % STAGES);
+            flush();
         }
-        store_block();
-        if (kb + 1 < kb_hi) load_block(kb + 1); // in flight while the tensor core works on this block
+        wait_stage(stage);                      // the MMAs that read this stage two blocks ago are done
+        store_block(stage, set_c);
+        if (kb + PF < kb_hi) load_block(kb + PF, set_c);        // in flight for the next PF blocks
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+            const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES), sa_lo = sa_hi + TILE_A, sb_hi = sa_lo + TILE_A, sb_lo = sb_hi + TILE_B;
 #pragma unroll
             for (int s = 0; s < CHUNKS / 2; ++s) {              // one MMA K-step = 8 TF32 values = 2 chunks
                 const uint64_t dah = umma_desc(sa_hi + 2 * s * CH_A, CH_A, 128), dal = umma_desc(sa_lo + 2 * s * CH_A, CH_A, 128);
@@ -243,11 +258,24 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
                 mma_tf32(tmem, dah, dbl, 1u);
                 mma_tf32(tmem, dal, dbh, 1u);
             }
-            umma_commit(&s_bar);                                // arrives when the MMAs above are complete
+            umma_commit(&s_bar[stage]);                         // arrives when every MMA issued so far is complete
         }
+        ++uses[stage];
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    static_assert(PF == 3, "the loop below rotates three register sets");
+    if (kb_lo < kb_hi) load_block(kb_lo, I0{});
+    if (kb_lo + 1 < kb_hi) load_block(kb_lo + 1, I1{});
+    if (kb_lo + 2 < kb_hi) load_block(kb_lo + 2, I2{});
+    for (int kb = kb_lo; kb < kb_hi; kb += 3) {
+        step(kb, I0{});
+        if (kb + 1 < kb_hi) step(kb + 1, I1{});
+        if (kb + 2 < kb_hi) step(kb + 2, I2{});
     }
     if (kb_lo < kb_hi) {
-        mbar_wait(&s_bar, parity);
+        wait_stage((kb_hi - 1 - kb_lo) % STAGES);
         flush();
         // epilogue: lane = mode m0 + 32*(warp%4) + lane-in-warp, column c = (beam, re/im)
         const int m = m0 + (warp & 3) * 32 + (tid & 31);

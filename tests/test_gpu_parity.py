@@ -395,3 +395,36 @@ def test_pass_lines_partial_slab_equals_full_pass():
                                        k * n // 2, n // 2, 1, 0.013, st))
     torch.cuda.synchronize()
     assert torch.equal(ref, out)
+
+
+# ----------------------------------------------------------------------------- tensor-core mode projection
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nb,nmodes,batch", [(128, 64, 130, 1), (256, 128, 96, 70), (256, 256, 200, 5)])
+def test_modes_project_tensor_core(n, nb, nmodes, batch):
+    """deconstruct_by_modes('scalar') on the tcgen05 path (complex64, 3xTF32): against the reference's
+    expression `modes_matrix @ flatten(crop(field))` (beam2d.py:592-600, no conjugate) in complex128,
+    1e-5 relative L2; ragged mode / beam counts (tiles of 128 modes x 64 beams are padded with zeros);
+    and against the SIMT kernel (LP2D_MODES_TC=0)."""
+    import os
+    rng = np.random.default_rng(n + nmodes)
+    modes = (rng.standard_normal((nmodes, nb * nb)) + 1j * rng.standard_normal((nmodes, nb * nb))).astype(np.complex64)
+    f0 = (rng.standard_normal((batch, n, n)) + 1j * rng.standard_normal((batch, n, n))).astype(np.complex64)
+    b = Beam2D(200 * um, n, 632 * nm, init_field=f0.copy(), complex_bits=64)
+    dn = (n - nb) // 2
+    crop = f0[:, dn:n - dn, dn:n - dn].reshape(batch, -1).astype(np.complex128)
+    exact = crop @ modes.astype(np.complex128).T                      # [beam][mode]
+    old = os.environ.get("LP2D_MODES_TC")
+    try:
+        os.environ["LP2D_MODES_TC"] = "1"
+        got = np.asarray(b.deconstruct_by_modes(modes))
+        os.environ["LP2D_MODES_TC"] = "0"
+        simt = np.asarray(b.deconstruct_by_modes(modes))
+    finally:
+        if old is None:
+            os.environ.pop("LP2D_MODES_TC", None)
+        else:
+            os.environ["LP2D_MODES_TC"] = old
+    assert got.shape == (batch, nmodes)
+    assert rel_l2(got, exact) <= 1e-5
+    assert rel_l2(simt, exact) <= 1e-5
+    assert rel_l2(got, simt) <= 1e-5
