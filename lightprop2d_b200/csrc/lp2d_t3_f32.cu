@@ -7,6 +7,8 @@ static const P2Ops<float> kT3F32[] = {
     T3Inst<float, 1024, 16, 4, 4>::entry(),
     T3Inst<float, 1024, 16, 8, 2>::entry(),
     T3Inst<float, 1024, 16, 2, 8>::entry(),
+    T5Inst<float, 1024, 16, 8, 2>::entry(),
+    T5Inst<float, 1024, 16, 4, 4>::entry(),
 };
 const P2Ops<float>* find_t3u_f32(int n, int variant) {
     int seen = 0;

@@ -920,6 +920,135 @@ __global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) t4_kernel(co
     if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
 }
 
+// --------------------------------------------------------------------------------------------
+// "T5": the ticket form with the register budget of the one-kernel-per-pass line kernels (E = 16 at
+// 1024 points, 64 registers, 2 x 512 threads per SM = 32 warps, scalar FP32 arithmetic).  Differences
+// to t3_item that keep it inside 64 registers: the inverse transform swaps re/im (register renaming,
+// free in scalar code) instead of mirroring the output index; the folded factor rows of the tile are
+// copied to shared memory once per item instead of being loaded next to the data.
+template <typename T, int N, int E, int W, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+__device__ __forceinline__ void t5_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, cx<T>* fbuf, int tid) {
+    using K = P2Cfg<T, N, E, W>;
+    constexpr int TPL = K::TPL;
+    constexpr long long PLANE = (long long)N * N;
+    constexpr long long PSTRIDE = (AXIS == AX_ROW) ? 1 : N;
+    constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CTA;
+    const P2Stage<T>& st = p.st[S];
+    const int l = (AXIS == AX_ROW) ? tid / TPL : tid % W;
+    const int t = (AXIS == AX_ROW) ? tid % TPL : tid / W;
+    cx<T>* sline = xbuf + l * K::LS;
+    const cx<T>* fline = fbuf + l * K::FL;
+    const long long b = it.g;                                   // G == 1: group = beam
+    const long long slot = it.g % p.ring_slots;
+    const int fixed = it.tile * W + l;
+    const long long off = ((AXIS == AX_ROW) ? (long long)fixed * N : fixed) + t * PSTRIDE;
+    const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
+
+    if (use_pre || MID) {
+        // the W folded factor rows of this tile (contiguous in the plane) -> shared memory
+        const float4* src = reinterpret_cast<const float4*>(p.fac + (long long)it.tile * W * K::FL);
+        float4* dst = reinterpret_cast<float4*>(fbuf);
+        for (int c = tid; c < W * K::FCH; c += K::THREADS) dst[c] = __ldcg(src + c);
+        __syncthreads();
+    }
+    const cx<T>* src = (IN_RING ? p.ring + slot * PLANE : st.in + b * PLANE) + off;
+    cx<T> v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = IN_RING ? __ldcg(src + (TPL * m) * PSTRIDE) : __ldcs(src + (TPL * m) * PSTRIDE);
+    if constexpr (!IN_RING) {
+        if (st.mask_kind != MASK_NONE) {
+            const long long mb = b * st.mask_beam_stride + off;
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (TPL * m) * PSTRIDE));
+        }
+        if (use_pre) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]);
+        }
+        if (st.out_pre != nullptr) {
+            cx<T>* dst = st.out_pre + b * PLANE + off;
+#pragma unroll
+            for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+        }
+    }
+    if constexpr (INV && !MID) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    }
+    line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+    if constexpr (MID) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(cmul(v[m], fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]));
+        if (st.out_mid != nullptr) {
+            cx<T>* dst = st.out_mid + b * PLANE + off;
+#pragma unroll
+            for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, cswap(v[m]));
+        }
+        line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+    }
+    if constexpr (INV || MID) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    }
+    if (st.scale != (T)1) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cscale(v[m], st.scale);
+    }
+    if constexpr (OUT_RING) {
+        cx<T>* dst = p.ring + slot * PLANE + off;
+#pragma unroll
+        for (int m = 0; m < E; ++m) p2_st_ring<2>(dst + (TPL * m) * PSTRIDE, v[m]);
+    } else {
+        if (st.out != nullptr) {
+            cx<T>* dst = st.out + b * PLANE + off;
+#pragma unroll
+            for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+        }
+        if (st.inten != nullptr) {
+            T* dst = st.inten + b * PLANE + off;
+#pragma unroll
+            for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m].x * v[m].x + v[m].y * v[m].y);
+        }
+    }
+}
+
+template <typename T, int N, int E, int W, int MINB>
+__global__ void __launch_bounds__(P2Cfg<T, N, E, W>::THREADS, MINB) t5_kernel(const __grid_constant__ P2Args<T> p) {
+    using K = P2Cfg<T, N, E, W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_item;
+    cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* fbuf = reinterpret_cast<cx<T>*>(smem_raw + K::SMEM_X);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int drawn = (int)atomicAdd(&p.counters[0], 1u);
+        P2Item it0;
+        if (drawn < p.total_items && p2_decode<T, K::TILES>(p, drawn, it0)) {
+            p2_wait_ready<T, K::TILES>(p, drawn, (unsigned)K::TILES);
+            s_item = drawn;
+        } else {
+            s_item = -1;
+        }
+    }
+    __syncthreads();
+    const int item = s_item;
+    if (item < 0) return;
+    P2Item it;
+    p2_decode<T, K::TILES>(p, item, it);
+    if (it.s == 0) {
+        if (p.st[0].inverse) t5_item<T, N, E, W, 0, AX_ROW, false, true, false, true>(p, it, xbuf, fbuf, tid);
+        else t5_item<T, N, E, W, 0, AX_ROW, false, true, false, false>(p, it, xbuf, fbuf, tid);
+    } else if (it.s == 1) {
+        if (p.st[1].mid) t5_item<T, N, E, W, 1, AX_COL, true, true, true, false>(p, it, xbuf, fbuf, tid);
+        else if (p.st[1].inverse) t5_item<T, N, E, W, 1, AX_COL, true, false, false, true>(p, it, xbuf, fbuf, tid);
+        else t5_item<T, N, E, W, 1, AX_COL, true, false, false, false>(p, it, xbuf, fbuf, tid);
+    } else {
+        t5_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, fbuf, tid);
+    }
+    __syncthreads();                                       // all stores of the item are issued
+    if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+}
+
 // The factor plane: fac[line][idx], idx = 0 .. N/2 (row stride FL).
 //   kind P2_FAC_H, by_column = 0: line = row j,    fac = H(a[idx], b[j])      (a[i] == a[N - i] bit for bit)
 //   kind P2_FAC_H, by_column = 1: line = column i, fac = H(a[i], b[idx])

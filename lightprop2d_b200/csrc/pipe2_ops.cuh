@@ -98,6 +98,30 @@ struct T4Inst {
     }
 };
 
+// t5_kernel: ticket form at the register budget of the line kernels (G = 1, factor rows in shared memory)
+template <typename T, int N, int E, int W, int MINB>
+struct T5Inst {
+    using K = P2Cfg<T, N, E, W>;
+    using LP = LinePlan<N, E>;
+    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void*, size_t) {
+        t5_kernel<T, N, E, W, MINB><<<grid, K::THREADS, K::SMEM_X + (need_factor ? K::SMEM_F : 0), s>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t configure(int* with_factor, int* plain) {
+        auto kern = t5_kernel<T, N, E, W, MINB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K::SMEM_X + K::SMEM_F));
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X + K::SMEM_F);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
+    }
+    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
+    static constexpr P2Ops<T> entry() {
+        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles, 2};
+    }
+};
+
 template <typename T, int N, int E, int W, int MINB>
 struct P2Inst {
     using K = P2Cfg<T, N, E, W>;

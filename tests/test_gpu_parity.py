@@ -428,3 +428,70 @@ def test_modes_project_tensor_core(n, nb, nmodes, batch):
     assert rel_l2(got, exact) <= 1e-5
     assert rel_l2(simt, exact) <= 1e-5
     assert rel_l2(got, simt) <= 1e-5
+
+
+# ----------------------------------------------------------------------------- fused step kernel: every entry
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,n", [(64, 256), (64, 512), (64, 1024), (128, 256), (128, 512)])
+def test_fused_step_paths_batched(bits, n):
+    """The sizes served by the fused step kernel (t3_kernel), batch of 3 beams, every step that stores
+    state: propagate (+z, -z), lens, coordinate_filter (bool generator mask, complex array mask) and
+    spectral_filter (real array mask -> the inverse two-stage chain with a mask at load), against the oracle."""
+    import ctypes as C
+    from lightprop2d_b200 import _lib as L
+    rng = np.random.default_rng(n + bits)
+    f0 = (rng.standard_normal((3, n, n)) + 1j * rng.standard_normal((3, n, n))).astype(CT[bits])
+    area, wl = 4e-1 * n / 1024, 532e-7
+    b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    name = C.create_string_buffer(200)
+    assert L.load().lp2d_plan_step_kernel(b._plan.handle, name, 200) == 1, name.value   # the fused kernel serves this plan
+    b.propagate(0.02); o.propagate(0.02)
+    b.lens(0.7); o.lens(0.7)
+    b.propagate(-0.013); o.propagate(-0.013)
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    b.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,)); o.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,))
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    cm = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(CT[bits])
+    b.coordinate_filter(f_init=cm.copy()); o.coordinate_filter(f_init=cm.copy())
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    rm = rng.uniform(size=(n, n))
+    b.spectral_filter(f_init=rm.copy()); o.spectral_filter(f_init=rm.copy())
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    b.propagate(0.5); o.propagate(0.5)
+    assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits]
+
+
+@pytest.mark.gpu
+def test_fused_step_equals_per_pass_kernels():
+    """LP2D_PIPE=0 (one kernel per pass) and the fused step kernel give the same state to rounding, for a
+    ragged batch (5 beams: the item queue has invalid fill / drain items) and a single beam."""
+    import os
+    import torch
+    from lightprop2d_b200 import beam2d as _b
+    res = {}
+    rng = np.random.default_rng(77)
+    f0 = (rng.standard_normal((5, 1024, 1024)) + 1j * rng.standard_normal((5, 1024, 1024))).astype(np.complex64)
+    old = os.environ.get("LP2D_PIPE")
+    try:
+        for mode in ("0", "2"):
+            os.environ["LP2D_PIPE"] = mode
+            _b._PLAN_CACHE.clear()
+            for nb in (5, 1):
+                b = Beam2D(4e-1, 1024, 532e-7, init_field=f0[:nb].copy(), complex_bits=64)
+                for z in (0.02, 0.02, -0.5):
+                    b.propagate(z)
+                res[(mode, nb)] = (np.asarray(b.field).copy(), np.asarray(b.spectrum).copy())
+    finally:
+        if old is None:
+            os.environ.pop("LP2D_PIPE", None)
+        else:
+            os.environ["LP2D_PIPE"] = old
+        _b._PLAN_CACHE.clear()
+    for nb in (5, 1):
+        assert rel_l2(res[("2", nb)][0], res[("0", nb)][0]) <= 2e-6
+        assert rel_l2(res[("2", nb)][1], res[("0", nb)][1]) <= 2e-6
+    torch.cuda.synchronize()
