@@ -243,9 +243,8 @@ int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
     if (name != nullptr && name_len > 0) {
         if (fused) {
             const int e = p->p2_32 ? p->p2_32->e : p->p2_64->e, w = p->p2_32 ? p->p2_32->w : p->p2_64->w;
-            const int kind = p->p2_32 ? p->p2_32->persistent : p->p2_64->persistent;
             snprintf(name, (size_t)name_len, "%s<%s, N=%d, E=%d, W=%d> fused step (rows -> L2 ring -> columns, one launch)",
-                     kind == 1 ? "p2_kernel" : kind == 2 ? "t4_kernel" : "t3_kernel", p->dtype == LP2D_C64 ? "float" : "double", p->n, e, w);
+                     "t3_kernel", p->dtype == LP2D_C64 ? "float" : "double", p->n, e, w);
         } else {
             const int e = p->ops32 ? p->ops32->e : p->ops64->e;
             snprintf(name, (size_t)name_len, "line_kernel<%s, N=%d, E=%d> row pass + column pass", p->dtype == LP2D_C64 ? "float" : "double", p->n, e);
@@ -322,11 +321,10 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     if (p->pipe_grid > 0 && p->pipe_grid < conc) conc = p->pipe_grid;
     const int tiles = ops->tiles;
     long long G = p->pipe_g > 0 ? p->pipe_g : 1;
-    if (ops->persistent == 2) G = 1;
     if (G > batch) G = batch;
     // lag (in groups) between consecutive stages of a group: the items in between cover every resident
-    // CTA twice (an item's dependencies are looked at one item ahead of its start)
-    const long long reach = ops->persistent == 1 ? 2 * conc : (5 * conc) / 4;
+    // CTA (with a margin), so that what an item depends on was drawn more than a wave earlier
+    const long long reach = (5 * conc) / 4;
     int lag = p->pipe_lag > 0 ? p->pipe_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles));
     if (lag < 1) lag = 1;
     // ring slots (groups): the stage that refills a slot must also be `lag` groups behind the last
@@ -370,7 +368,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "fused step: batch too large for one launch");
         a.total_items = (int)total;
         LP2D_CU(cudaMemsetAsync(p->counters, 0, sizeof(unsigned int) * (1 + (size_t)nstages * a.ngroups), s), "fused step counters");
-        const unsigned grid = ops->persistent == 1 ? (unsigned)(total < conc ? total : conc) : (unsigned)total;
+        const unsigned grid = (unsigned)total;      // one CTA per item
         LP2D_CU(ops->launch(a, grid, need_factor, s, p->ring, p->pipe_persist ? (size_t)(slots * G * plane) : 0), "fused step launch");
     }
     return LP2D_OK;

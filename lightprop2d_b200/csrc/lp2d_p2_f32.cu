@@ -4,23 +4,15 @@
 
 namespace lp2d {
 static const P2Ops<float> kP2F32[] = {
-    // variant 0 of each size is the default (measured best, profiles/r1c_*)
+    // the first entry of each size is the default (measured best, profiles/r1c_size_sweep.log)
     T3Inst<float, 1024, 32, 8, 2>::entry(),
     T3Inst<float, 1024, 32, 4, 3>::entry(),
-    T3Inst<float, 1024, 32, 4, 4>::entry(),
-    T3Inst<float, 1024, 32, 2, 6>::entry(),
-    T4Inst<float, 1024, 32, 4, 2, 3>::entry(),
-    P2Inst<float, 1024, 32, 4, 4>::entry(),
-    P2Inst<float, 1024, 32, 4, 3>::entry(),
     T3Inst<float, 512, 32, 8, 3>::entry(),
-    T3Inst<float, 512, 16, 8, 4>::entry(),
     T3Inst<float, 512, 32, 16, 2>::entry(),
     T3Inst<float, 256, 16, 16, 4>::entry(),
     T3Inst<float, 256, 16, 8, 8>::entry(),
 };
-const P2Ops<float>* find_t3u_f32(int n, int variant);
 const P2Ops<float>* find_p2_f32(int n, int variant) {
-    if (variant >= 10) return find_t3u_f32(n, variant - 10);
     const P2Ops<float>* first = nullptr;
     int seen = 0;
     for (const auto& o : kP2F32) {

@@ -1,4 +1,4 @@
-// Host-side entry of one (T, N, E, W) instance of the fused step kernel (pipe2.cuh).
+// Host-side entry of one (T, N, E, W) instance of the fused step kernel (pipe2.cuh, t3_kernel).
 #pragma once
 #include <cmath>
 #include <cuda_runtime.h>
@@ -14,15 +14,14 @@ struct P2Ops {
     int threads;
     int fl;             // factor-plane row stride (samples)
     int tw_size;        // twiddle table entries of LinePlan<n, e>
-    size_t smem_x;      // exchange / landing area
-    size_t smem_f;      // factor rows, only for steps that need them
+    size_t smem_x;      // exchange area
+    size_t smem_f;      // unused (the factor rows are read from the L2-resident plane)
     // win_ptr / win_bytes: optional L2 persisting access window (the ring); win_bytes = 0: none
     cudaError_t (*launch)(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void* win_ptr,
                           size_t win_bytes);
     // opt in to large dynamic shared memory; resident CTAs per SM with / without the factor rows
     cudaError_t (*configure)(int* ctas_per_sm_factor, int* ctas_per_sm_plain);
     void (*twiddles)(std::vector<double>& re_im);
-    int persistent;     // 1: p2_kernel (grid = resident CTAs), 0: t3_kernel, 2: t4_kernel (grid = items, G = 1)
 };
 
 const P2Ops<float>* find_p2_f32(int n, int variant);
@@ -50,7 +49,6 @@ void p2_twiddles(std::vector<double>& w) {
     }
 }
 
-// ticket form (t3_kernel): same P2Ops record; grid = number of items (flagged by persistent = 0)
 template <typename T, int N, int E, int W, int MINB>
 struct T3Inst {
     using K = T3Cfg<T, N, E, W>;
@@ -70,93 +68,7 @@ struct T3Inst {
     }
     static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
     static constexpr P2Ops<T> entry() {
-        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, 0, &launch, &configure, &twiddles, 0};
-    }
-};
-
-// ticket form with staged tiles (t4_kernel): items of TG tiles of one beam (G is forced to 1)
-template <typename T, int N, int E, int W, int TG, int MINB>
-struct T4Inst {
-    using K = P2Cfg<T, N, E, W>;
-    using LP = LinePlan<N, E>;
-    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void*, size_t) {
-        t4_kernel<T, N, E, W, TG, MINB><<<grid, K::THREADS, K::SMEM_X + (need_factor ? K::SMEM_F : 0), s>>>(a);
-        ++g_launches;
-        return cudaGetLastError();
-    }
-    static cudaError_t configure(int* with_factor, int* plain) {
-        auto kern = t4_kernel<T, N, E, W, TG, MINB>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K::SMEM_X + K::SMEM_F));
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X + K::SMEM_F);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
-    }
-    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
-    static constexpr P2Ops<T> entry() {
-        return P2Ops<T>{N, E, W, K::TILES / TG, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles, 2};
-    }
-};
-
-// t5_kernel: ticket form at the register budget of the line kernels (G = 1, factor rows in shared memory)
-template <typename T, int N, int E, int W, int MINB>
-struct T5Inst {
-    using K = P2Cfg<T, N, E, W>;
-    using LP = LinePlan<N, E>;
-    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void*, size_t) {
-        t5_kernel<T, N, E, W, MINB><<<grid, K::THREADS, K::SMEM_X + (need_factor ? K::SMEM_F : 0), s>>>(a);
-        ++g_launches;
-        return cudaGetLastError();
-    }
-    static cudaError_t configure(int* with_factor, int* plain) {
-        auto kern = t5_kernel<T, N, E, W, MINB>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K::SMEM_X + K::SMEM_F));
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X + K::SMEM_F);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
-    }
-    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
-    static constexpr P2Ops<T> entry() {
-        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles, 2};
-    }
-};
-
-template <typename T, int N, int E, int W, int MINB>
-struct P2Inst {
-    using K = P2Cfg<T, N, E, W>;
-    using LP = LinePlan<N, E>;
-    static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool need_factor, cudaStream_t s, void* win_ptr,
-                              size_t win_bytes) {
-        const size_t smem = K::SMEM_X + (need_factor ? K::SMEM_F : 0);
-        ++g_launches;
-        if (win_bytes == 0) {
-            p2_kernel<T, N, E, W, MINB><<<grid, K::THREADS, smem, s>>>(a);
-            return cudaGetLastError();
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(K::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = win_ptr;
-        attr[0].val.accessPolicyWindow.num_bytes = win_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, p2_kernel<T, N, E, W, MINB>, a);
-    }
-    static cudaError_t configure(int* with_factor, int* plain) {
-        auto kern = p2_kernel<T, N, E, W, MINB>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(K::SMEM_X + K::SMEM_F));
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X + K::SMEM_F);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(plain, kern, K::THREADS, K::SMEM_X);
-    }
-    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
-    static constexpr P2Ops<T> entry() {
-        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, K::SMEM_F, &launch, &configure, &twiddles, 1};
+        return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, 0, &launch, &configure, &twiddles};
     }
 };
 
