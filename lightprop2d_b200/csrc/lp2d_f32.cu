@@ -16,8 +16,12 @@ static const SizeOps<float> kOpsF32[] = {
     Ops<float, 1024, 32, 8, 4>::entry(4),
     Ops<float, 1024, 32, 8, 16>::entry(5),
     Ops<float, 2048, 16, 2, 4>::entry(),
-    Ops<float, 4096, 16, 1, 2>::entry(),
-    Ops<float, 8192, 16, 1, 1>::entry(),
+    Ops<float, 2048, 16, 2, 8>::entry(1),
+    // large grids: the widest column tile that fits 1024 threads (measured: profiles/r1c_large_n_variants.log)
+    Ops<float, 4096, 16, 1, 4>::entry(),
+    Ops<float, 4096, 16, 1, 2>::entry(1),
+    Ops<float, 8192, 16, 1, 2>::entry(),
+    Ops<float, 8192, 16, 1, 1>::entry(1),
 };
 const SizeOps<float>* find_ops_f32(int n, int variant) {
     const SizeOps<float>* first = nullptr;

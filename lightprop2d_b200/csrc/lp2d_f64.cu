@@ -10,8 +10,11 @@ static const SizeOps<double> kOpsF64[] = {
     Ops<double, 256, 8, 8, 8>::entry(),
     Ops<double, 512, 8, 4, 4>::entry(),
     Ops<double, 1024, 8, 2, 4>::entry(),
+    Ops<double, 1024, 8, 2, 8>::entry(1),
     Ops<double, 2048, 8, 1, 2>::entry(),
-    Ops<double, 4096, 8, 1, 1>::entry(),
+    Ops<double, 2048, 8, 1, 4>::entry(1),
+    Ops<double, 4096, 8, 1, 2>::entry(),
+    Ops<double, 4096, 8, 1, 1>::entry(1),
 };
 const SizeOps<double>* find_ops_f64(int n, int variant) {
     const SizeOps<double>* first = nullptr;

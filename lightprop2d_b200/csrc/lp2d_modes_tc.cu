@@ -24,10 +24,12 @@
 // mode tile and the field tile from HBM (coalesced 16-byte loads, issued one block ahead), split /
 // combine them in registers, and write the four operand tiles to one of two shared-memory stages in
 // the canonical no-swizzle K-major UMMA layout ([16-byte K chunk][row], chunk stride padded by 16
-// bytes against bank conflicts); one thread issues the 12 tcgen05.mma of the block and commits them
-// to the stage's mbarrier, which the next overwrite of that stage waits on -- so the tensor core
-// works on block k while the threads stage block k+1.
+// bytes against bank conflicts) and hand the stage to a ninth warp through a "full" mbarrier; that warp
+// issues the 12 tcgen05.mma of the block and commits them to the stage's "empty" mbarrier, which the
+// next overwrite of the stage waits on -- the tensor core works on block k while the producers stage
+// block k+1, and issuing MMAs never delays the staging.
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <type_traits>
 
@@ -45,9 +47,10 @@ constexpr int BT = 64;             // beams per tile
 constexpr int UN = 2 * BT;         // UMMA N
 constexpr int KB = 16;             // complex samples per K block
 constexpr int CHUNKS = KB / 2;     // 16-byte K chunks per row and block (4 TF32 values = 2 complex samples)
-constexpr int THREADS = 256;
+constexpr int THREADS = 256;       // producer / epilogue threads (warps 0..7); warp 8 issues the MMAs
+constexpr int CTA_THREADS = THREADS + 32;
 constexpr int FLUSH = 8;            // K blocks per TMEM accumulation chain
-constexpr int PF = 3;               // K blocks of global loads in flight per thread (register sets)
+constexpr int PF = 2;               // K blocks of global loads in flight per thread (register sets)
 constexpr int STAGES = 2;           // operand tile sets in shared memory (the stores of block k+1 overlap the MMAs of block k)
 constexpr int ACC = UN / 2;         // accumulator columns per thread: warp w owns lanes 32*(w%4).., columns ACC*(w/4)..
 constexpr int CH_A = UM * 16 + 16; // byte stride between K chunks of the A tiles (padded)
@@ -121,11 +124,13 @@ struct Args {
     int kblocks;            // nb*nb / KB
     int ksplit;             // CTAs along the reduction
     int mtiles, btiles;
+    int nmma;               // debug: 3 = 3xTF32 (product), 1 = hi*hi only (timing experiments)
 };
 
-__global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args p) {
+__global__ void __launch_bounds__(CTA_THREADS, 1) modes_project_tc_kernel(const Args p) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t s_bar[STAGES];
+    __shared__ uint64_t s_full[STAGES];      // producers -> MMA warp: the stage holds block i
+    __shared__ uint64_t s_empty[STAGES];     // tcgen05.commit -> producers: the MMAs that read the stage are done
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
     const int kb_lo = (int)((long long)p.kblocks * ks / p.ksplit), kb_hi = (int)((long long)p.kblocks * (ks + 1) / p.ksplit);
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -225,57 +230,60 @@ __global__ void __launch_bounds__(THREADS, 1) modes_project_tc_kernel(const Args
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    // commits issued so far on each stage's mbarrier; the latest one is phase uses - 1
-    int uses[STAGES];
+    // Block i (0-based in this CTA's range) lives in stage i % STAGES; it is the (i / STAGES)-th use of the
+    // stage, so both of the stage's mbarriers complete phase i / STAGES for it (parity (i / STAGES) & 1).
+    const int nblocks = kb_hi - kb_lo;
+    if (warp == THREADS / 32) {
+        // ===== MMA issuer (one lane) =====
+        if ((tid & 31) == 0) {
+            for (int i = 0; i < nblocks; ++i) {
+                const int stage = i % STAGES;
+                const bool fresh = (i % FLUSH) == 0;                 // this block starts a new accumulation chain
+                mbar_wait(&s_full[stage], (uint32_t)((i / STAGES) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES), sa_lo = sa_hi + TILE_A, sb_hi = sa_lo + TILE_A, sb_lo = sb_hi + TILE_B;
 #pragma unroll
-    for (int i = 0; i < STAGES; ++i) uses[i] = 0;
-    auto wait_stage = [&](int stage) {
-        if (uses[stage] > 0) mbar_wait(&s_bar[stage], (uint32_t)((uses[stage] - 1) & 1));
-    };
-    // one K block: stage the register set SET (loaded PF blocks ago), refill it, multiply
-    auto step = [&](int kb, auto set_c) {
-        const int stage = (kb - kb_lo) % STAGES;
-        const bool fresh = ((kb - kb_lo) % FLUSH) == 0;          // this block starts a new accumulation chain
-        if (fresh && kb > kb_lo) {
-            // the chain closed by the previous block is complete (a commit covers every earlier MMA)
-            wait_stage((kb - 1 - kb_lo) % STAGES);
-            flush();
-        }
-        wait_stage(stage);                      // the MMAs that read this stage two blocks ago are done
-        store_block(stage, set_c);
-        if (kb + PF < kb_hi) load_block(kb + PF, set_c);        // in flight for the next PF blocks
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES), sa_lo = sa_hi + TILE_A, sb_hi = sa_lo + TILE_A, sb_lo = sb_hi + TILE_B;
-#pragma unroll
-            for (int s = 0; s < CHUNKS / 2; ++s) {              // one MMA K-step = 8 TF32 values = 2 chunks
-                const uint64_t dah = umma_desc(sa_hi + 2 * s * CH_A, CH_A, 128), dal = umma_desc(sa_lo + 2 * s * CH_A, CH_A, 128);
-                const uint64_t dbh = umma_desc(sb_hi + 2 * s * CH_B, CH_B, 128), dbl = umma_desc(sb_lo + 2 * s * CH_B, CH_B, 128);
-                mma_tf32(tmem, dah, dbh, (!fresh || s > 0) ? 1u : 0u);
-                mma_tf32(tmem, dah, dbl, 1u);
-                mma_tf32(tmem, dal, dbh, 1u);
+                for (int s = 0; s < CHUNKS / 2; ++s) {              // one MMA K-step = 8 TF32 values = 2 chunks
+                    const uint64_t dah = umma_desc(sa_hi + 2 * s * CH_A, CH_A, 128), dal = umma_desc(sa_lo + 2 * s * CH_A, CH_A, 128);
+                    const uint64_t dbh = umma_desc(sb_hi + 2 * s * CH_B, CH_B, 128), dbl = umma_desc(sb_lo + 2 * s * CH_B, CH_B, 128);
+                    mma_tf32(tmem, dah, dbh, (!fresh || s > 0) ? 1u : 0u);
+                    if (p.nmma == 3) {
+                        mma_tf32(tmem, dah, dbl, 1u);
+                        mma_tf32(tmem, dal, dbh, 1u);
+                    }
+                }
+                umma_commit(&s_empty[stage]);                       // arrives when every MMA issued so far is complete
             }
-            umma_commit(&s_bar[stage]);                         // arrives when every MMA issued so far is complete
         }
-        ++uses[stage];
-    };
-    using I0 = std::integral_constant<int, 0>;
-    using I1 = std::integral_constant<int, 1>;
-    using I2 = std::integral_constant<int, 2>;
-    static_assert(PF == 3, "the loop below rotates three register sets");
-    if (kb_lo < kb_hi) load_block(kb_lo, I0{});
-    if (kb_lo + 1 < kb_hi) load_block(kb_lo + 1, I1{});
-    if (kb_lo + 2 < kb_hi) load_block(kb_lo + 2, I2{});
-    for (int kb = kb_lo; kb < kb_hi; kb += 3) {
-        step(kb, I0{});
-        if (kb + 1 < kb_hi) step(kb + 1, I1{});
-        if (kb + 2 < kb_hi) step(kb + 2, I2{});
+    } else {
+        // ===== producers: stage the register set SET (loaded PF blocks ago), refill it, hand the stage over =====
+        auto step = [&](int i, auto set_c) {
+            const int stage = i % STAGES;
+            if ((i % FLUSH) == 0 && i > 0) {
+                // the chain closed by block i-1 is complete (a commit covers every earlier MMA); the MMA warp
+                // cannot start the next chain before this block is handed over below
+                mbar_wait(&s_empty[(i - 1) % STAGES], (uint32_t)(((i - 1) / STAGES) & 1));
+                flush();
+            }
+            if (i >= STAGES) mbar_wait(&s_empty[stage], (uint32_t)((i / STAGES - 1) & 1));   // the stage's previous block was multiplied
+            store_block(stage, set_c);
+            if (i + PF < nblocks) load_block(kb_lo + i + PF, set_c);     // in flight for the next PF blocks
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");      // all producers have written the stage
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[stage])) : "memory");
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        static_assert(PF == 2, "the loop below rotates two register sets");
+        if (0 < nblocks) load_block(kb_lo, I0{});
+        if (1 < nblocks) load_block(kb_lo + 1, I1{});
+        for (int i = 0; i < nblocks; i += 2) {
+            step(i, I0{});
+            if (i + 1 < nblocks) step(i + 1, I1{});
+        }
     }
-    if (kb_lo < kb_hi) {
-        wait_stage((kb_hi - 1 - kb_lo) % STAGES);
+    if (nblocks > 0 && warp < THREADS / 32) {
+        mbar_wait(&s_empty[(nblocks - 1) % STAGES], (uint32_t)(((nblocks - 1) / STAGES) & 1));
         flush();
         // epilogue: lane = mode m0 + 32*(warp%4) + lane-in-warp, column c = (beam, re/im)
         const int m = m0 + (warp & 3) * 32 + (tid & 31);
@@ -324,9 +332,10 @@ int modes_project_tc(const void* field, const void* modes, void* coeffs, int n, 
     if (ksplit > a.kblocks) ksplit = a.kblocks;
     if (ksplit < 1) ksplit = 1;
     a.ksplit = ksplit;
+    { const char* dbg = getenv("LP2D_TC_DEBUG_NMMA"); a.nmma = (dbg != nullptr && atoi(dbg) == 1) ? 1 : 3; }
     cudaError_t e = cudaMemsetAsync(coeffs, 0, sizeof(float2) * (size_t)batch * nmodes, s);
     if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project_tc memset: ") + cudaGetErrorString(e));
-    modes_project_tc_kernel<<<(unsigned)(tiles * ksplit), THREADS, SMEM_BYTES, s>>>(a);
+    modes_project_tc_kernel<<<(unsigned)(tiles * ksplit), CTA_THREADS, SMEM_BYTES, s>>>(a);
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project_tc launch: ") + cudaGetErrorString(e));
