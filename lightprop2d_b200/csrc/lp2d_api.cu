@@ -222,7 +222,12 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     env = getenv("LP2D_PIPE_HINTS"); p->pipe_hints = env ? atoi(env) : 3;
     // measured (profiles/r1c_size_sweep.log): the fused kernel wins on the steps that read AND write state
     // (3*P*B algorithmic bytes); plain fft2 and the three-stage fresh chain stay on the per-pass kernels
-    env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : 2;
+    // and, for the small planes, on more of them (profiles/r1c_size_sweep.log, r1c_group_sweep.log):
+    //   complex64 256: + plain fft2; complex64 512 and complex128 256: every step
+    int ops_default = 2;
+    if (dtype == LP2D_C64 && n == 256) ops_default = 3;
+    if ((dtype == LP2D_C64 && n == 512) || (dtype == LP2D_C128 && n == 256)) ops_default = 7;
+    env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : ops_default;
     env = getenv("LP2D_PIPE_PERSIST"); p->pipe_persist = env ? atoi(env) : 0;
     if (p->pipe_persist && p->ring != nullptr) {
         cudaDeviceProp prop;
@@ -320,7 +325,9 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     long long conc = (long long)ctas * p->num_sms;
     if (p->pipe_grid > 0 && p->pipe_grid < conc) conc = p->pipe_grid;
     const int tiles = ops->tiles;
-    long long G = p->pipe_g > 0 ? p->pipe_g : 1;
+    // beams per work item: two for planes of up to 512 points (halves the per-item overhead; the ring still
+    // fits L2), one for 1024 points (the ring would double to 64 MB)
+    long long G = p->pipe_g > 0 ? p->pipe_g : (p->n <= 512 ? 2 : 1);
     if (G > batch) G = batch;
     // lag (in groups) between consecutive stages of a group: the items in between cover every resident
     // CTA (with a margin), so that what an item depends on was drawn more than a wave earlier
