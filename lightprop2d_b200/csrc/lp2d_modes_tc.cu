@@ -20,11 +20,11 @@
 // -- round to nearest -- to FP32 registers, and the next MMA starts a fresh chain; at the end the
 // register sums are added to the zero-initialised output with FP32 atomics (red.global.add.f32).
 //
-// Per K block (16 complex samples = 32 TF32 values per row = 4 MMA K-steps): the 256 threads copy the
+// Per K block (16 complex samples = 32 TF32 values per row = 4 MMA K-steps): the 512 producer threads copy the
 // mode tile and the field tile from HBM (coalesced 16-byte loads, issued one block ahead), split /
 // combine them in registers, and write the four operand tiles to one of two shared-memory stages in
 // the canonical no-swizzle K-major UMMA layout ([16-byte K chunk][row], chunk stride padded by 16
-// bytes against bank conflicts) and hand the stage to a ninth warp through a "full" mbarrier; that warp
+// bytes against bank conflicts) and hand the stage to a seventeenth warp through a "full" mbarrier; that warp
 // issues the 12 tcgen05.mma of the block and commits them to the stage's "empty" mbarrier, which the
 // next overwrite of the stage waits on -- the tensor core works on block k while the producers stage
 // block k+1, and issuing MMAs never delays the staging.
@@ -47,12 +47,12 @@ constexpr int BT = 64;             // beams per tile
 constexpr int UN = 2 * BT;         // UMMA N
 constexpr int KB = 16;             // complex samples per K block
 constexpr int CHUNKS = KB / 2;     // 16-byte K chunks per row and block (4 TF32 values = 2 complex samples)
-constexpr int THREADS = 256;       // producer / epilogue threads (warps 0..7); warp 8 issues the MMAs
+constexpr int THREADS = 512;       // producer / epilogue threads (warps 0..15); warp 16 issues the MMAs
 constexpr int CTA_THREADS = THREADS + 32;
 constexpr int FLUSH = 8;            // K blocks per TMEM accumulation chain
 constexpr int PF = 2;               // K blocks of global loads in flight per thread (register sets)
 constexpr int STAGES = 2;           // operand tile sets in shared memory (the stores of block k+1 overlap the MMAs of block k)
-constexpr int ACC = UN / 2;         // accumulator columns per thread: warp w owns lanes 32*(w%4).., columns ACC*(w/4)..
+constexpr int ACC = UN / (THREADS / 128);   // accumulator columns per thread: warp w owns lanes 32*(w%4).., columns ACC*(w/4)..
 constexpr int CH_A = UM * 16 + 16; // byte stride between K chunks of the A tiles (padded)
 constexpr int CH_B = UN * 16 + 16;
 constexpr int TILE_A = CHUNKS * CH_A;
@@ -155,25 +155,43 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) modes_project_tc_kernel(const 
     const int dn = (p.n - p.nb) / 2;
     const long long kk = (long long)p.nb * p.nb;
     // per-thread load assignment: piece q = tid + THREADS*i -> (row, chunk) = (q / CHUNKS, q % CHUNKS):
-    // 16 consecutive threads read the 256 contiguous bytes of one row of the block
+    // 8 consecutive threads read the 128 contiguous bytes of one row of the block.  Everything that does
+    // not change from block to block is computed once: the global row origins, the shared-memory
+    // offsets and the validity of the rows; a block then costs one pointer offset per load.
+    const float4* pa[A_LD];            // mode rows: origin of chunk c of row (m0 + row) at crop sample 0
+    uint32_t oa[A_LD];                 // byte offset of (chunk, row) inside an A tile
+    bool va[A_LD];
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+        const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
+        va[i] = (m0 + row < p.nmodes);
+        pa[i] = reinterpret_cast<const float4*>(p.modes + (long long)(va[i] ? m0 + row : 0) * kk) + c;
+        oa[i] = (uint32_t)(c * CH_A + row * 16);
+    }
+    const float4* pb[B_LD];            // field planes: origin of chunk c of beam (b0 + row) at crop sample (0, 0)
+    uint32_t ob[B_LD];                 // byte offset of (chunk, beam row pair) inside a B tile
+    bool vb[B_LD];
+#pragma unroll
+    for (int i = 0; i < B_LD; ++i) {
+        const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
+        vb[i] = (b0 + row < p.batch);
+        pb[i] = reinterpret_cast<const float4*>(p.field + ((long long)(vb[i] ? b0 + row : 0) * p.n + dn) * p.n + dn) + c;
+        ob[i] = (uint32_t)(c * CH_B + (2 * row) * 16);
+    }
+    // position of the next block to LOAD, advanced incrementally (KB divides nb: a block stays in one crop row)
+    long long ld_a = (long long)kb_lo * KB / 2;                              // float4 offset along a mode row
+    int ld_cy = (int)(((long long)kb_lo * KB) / p.nb), ld_cx = (int)(((long long)kb_lo * KB) % p.nb);
     float4 ra[PF][A_LD], rb[PF][B_LD];
-    auto load_block = [&](int kb, auto set_c) {
+    auto load_block = [&](auto set_c) {
         constexpr int SET = decltype(set_c)::value;
-        const long long p0 = (long long)kb * KB;                 // first crop sample of the block
-        const int cy = (int)(p0 / p.nb), cx0 = (int)(p0 % p.nb); // KB divides nb: a block stays in one crop row
+        const long long ld_b = ((long long)ld_cy * p.n + ld_cx) / 2;         // float4 offset inside the field plane
 #pragma unroll
-        for (int i = 0; i < A_LD; ++i) {
-            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
-            ra[SET][i] = (m0 + row < p.nmodes) ? __ldcs(reinterpret_cast<const float4*>(p.modes + (long long)(m0 + row) * kk + p0) + c)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < A_LD; ++i) ra[SET][i] = va[i] ? __ldcs(pa[i] + ld_a) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < B_LD; ++i) {
-            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
-            rb[SET][i] = (b0 + row < p.batch)
-                        ? __ldg(reinterpret_cast<const float4*>(p.field + ((long long)(b0 + row) * p.n + dn + cy) * p.n + dn + cx0) + c)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < B_LD; ++i) rb[SET][i] = vb[i] ? __ldg(pb[i] + ld_b) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ld_a += KB / 2;
+        ld_cx += KB;
+        if (ld_cx >= p.nb) { ld_cx = 0; ++ld_cy; }
     };
     auto store_block = [&](int stage, auto set_c) {
         constexpr int SET = decltype(set_c)::value;
@@ -183,26 +201,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) modes_project_tc_kernel(const 
         unsigned char* b_lo = b_hi + TILE_B;
 #pragma unroll
         for (int i = 0; i < A_LD; ++i) {
-            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
             float4 h, l;
             split_tf32(ra[SET][i].x, h.x, l.x); split_tf32(ra[SET][i].y, h.y, l.y);
             split_tf32(ra[SET][i].z, h.z, l.z); split_tf32(ra[SET][i].w, h.w, l.w);
-            *reinterpret_cast<float4*>(a_hi + c * CH_A + row * 16) = h;
-            *reinterpret_cast<float4*>(a_lo + c * CH_A + row * 16) = l;
+            *reinterpret_cast<float4*>(a_hi + oa[i]) = h;
+            *reinterpret_cast<float4*>(a_lo + oa[i]) = l;
         }
 #pragma unroll
         for (int i = 0; i < B_LD; ++i) {
-            const int q = tid + THREADS * i, row = q / CHUNKS, c = q % CHUNKS;
-            // two complex samples (x, y), (z, w) of beam `row`: row 2b = (Fr, -Fi), row 2b+1 = (Fi, Fr)
-            const float4 f = rb[SET][i];
-            const float4 re = make_float4(f.x, -f.y, f.z, -f.w), im = make_float4(f.y, f.x, f.w, f.z);
+            // two complex samples (x, y), (z, w) of a beam: row 2b = (Fr, -Fi), row 2b+1 = (Fi, Fr); the
+            // split commutes with the sign and the permutation, so every value is split once
             float4 h, l;
-            split_tf32(re.x, h.x, l.x); split_tf32(re.y, h.y, l.y); split_tf32(re.z, h.z, l.z); split_tf32(re.w, h.w, l.w);
-            *reinterpret_cast<float4*>(b_hi + c * CH_B + (2 * row) * 16) = h;
-            *reinterpret_cast<float4*>(b_lo + c * CH_B + (2 * row) * 16) = l;
-            split_tf32(im.x, h.x, l.x); split_tf32(im.y, h.y, l.y); split_tf32(im.z, h.z, l.z); split_tf32(im.w, h.w, l.w);
-            *reinterpret_cast<float4*>(b_hi + c * CH_B + (2 * row + 1) * 16) = h;
-            *reinterpret_cast<float4*>(b_lo + c * CH_B + (2 * row + 1) * 16) = l;
+            split_tf32(rb[SET][i].x, h.x, l.x); split_tf32(rb[SET][i].y, h.y, l.y);
+            split_tf32(rb[SET][i].z, h.z, l.z); split_tf32(rb[SET][i].w, h.w, l.w);
+            *reinterpret_cast<float4*>(b_hi + ob[i]) = make_float4(h.x, -h.y, h.z, -h.w);
+            *reinterpret_cast<float4*>(b_lo + ob[i]) = make_float4(l.x, -l.y, l.z, -l.w);
+            *reinterpret_cast<float4*>(b_hi + ob[i] + 16) = make_float4(h.y, h.x, h.w, h.z);
+            *reinterpret_cast<float4*>(b_lo + ob[i] + 16) = make_float4(l.y, l.x, l.w, l.z);
         }
     };
 
@@ -267,7 +282,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) modes_project_tc_kernel(const 
             }
             if (i >= STAGES) mbar_wait(&s_empty[stage], (uint32_t)((i / STAGES - 1) & 1));   // the stage's previous block was multiplied
             store_block(stage, set_c);
-            if (i + PF < nblocks) load_block(kb_lo + i + PF, set_c);     // in flight for the next PF blocks
+            if (i + PF < nblocks) load_block(set_c);                    // in flight for the next PF blocks
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
             asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");      // all producers have written the stage
             if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[stage])) : "memory");
@@ -275,8 +290,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) modes_project_tc_kernel(const 
         using I0 = std::integral_constant<int, 0>;
         using I1 = std::integral_constant<int, 1>;
         static_assert(PF == 2, "the loop below rotates two register sets");
-        if (0 < nblocks) load_block(kb_lo, I0{});
-        if (1 < nblocks) load_block(kb_lo + 1, I1{});
+        if (0 < nblocks) load_block(I0{});
+        if (1 < nblocks) load_block(I1{});
         for (int i = 0; i < nblocks; i += 2) {
             step(i, I0{});
             if (i + 1 < nblocks) step(i + 1, I1{});
