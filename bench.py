@@ -303,14 +303,14 @@ def run_ours(args):
     host_out = torch.empty(E2E_BEAMS, n, n, dtype=torch.float32, pin_memory=True)
     Ke = max(3, min(K, 10))
     for _ in range(2):
-        prop.intensity_from_host(host_in, DZ, chunk=16, out=host_out)
+        prop.intensity_from_host(host_in, DZ, chunk=8, out=host_out)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(Ke):
-        prop.intensity_from_host(host_in, DZ, chunk=16, out=host_out)
+        prop.intensity_from_host(host_in, DZ, chunk=8, out=host_out)
     b_.record()
     torch.cuda.synchronize()
     e2e_ms = max(a.elapsed_time(b_), (time.perf_counter() - t0) * 1e3)

@@ -70,6 +70,8 @@ struct lp2d_plan {
     void* p2_fac;              // factor plane [n][fl]
     int fac_kind, fac_by_column;   // what p2_fac currently holds (0 = nothing)
     double fac_p0, fac_p1;
+    cudaEvent_t p2_done;       // end of the last fused launch: the ring, the counters and the factor plane are
+                               // plan state, so fused launches of one plan are serialised across streams
 };
 
 #define LP2D_CHECK_PLAN(p)                                                      \
@@ -177,7 +179,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         return cuda_fail(e, "cudaMemcpy(tables)");
     }
     p->ring = nullptr; p->counters = nullptr; p->ring_bytes = 0; p->counters_cap = 0; p->num_sms = 0;
-    p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0;
+    p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
     if (env == nullptr || atoi(env) == 2) {
@@ -199,6 +201,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * p->counters_cap);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_tw, n2 * csz);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_fac, (size_t)n * (q32 ? q32->fl : q64->fl) * csz);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->p2_done, cudaEventDisableTiming);
             if (e == cudaSuccess) {
                 if (dtype == LP2D_C64) {
                     std::vector<float> wf(w2.size());
@@ -266,6 +269,7 @@ int lp2d_plan_destroy(lp2d_plan* p) {
     cudaFree(p->counters);
     cudaFree(p->p2_tw);
     cudaFree(p->p2_fac);
+    if (p->p2_done) cudaEventDestroy(p->p2_done);
     if (p->nstreams > 1) {
         for (int i = 0; i < p->nstreams; ++i) { cudaStreamDestroy(p->aux[i]); cudaEventDestroy(p->ev_join[i]); }
         cudaEventDestroy(p->ev_fork);
@@ -340,6 +344,8 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     if (p->pipe_slots > 0) slots = p->pipe_slots > (nstages - 1) * lag + 1 ? p->pipe_slots : (nstages - 1) * lag + 1;
     while (G > 1 && slots * G * plane > p->ring_bytes) --G;
     if (slots * G * plane > p->ring_bytes) return -1;
+    // wait for the previous fused launch of this plan, whichever stream it ran on
+    LP2D_CU(cudaStreamWaitEvent(s, p->p2_done, 0), "fused step: wait for the previous launch");
     if (need_factor) {
         const int rc = p2_ensure_factor<T>(p, fac_kind, by_column, p0, p1, s);
         if (rc) return rc;
@@ -378,6 +384,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         const unsigned grid = (unsigned)total;      // one CTA per item
         LP2D_CU(ops->launch(a, grid, need_factor, s, p->ring, p->pipe_persist ? (size_t)(slots * G * plane) : 0), "fused step launch");
     }
+    LP2D_CU(cudaEventRecord(p->p2_done, s), "fused step: record completion");
     return LP2D_OK;
 }
 

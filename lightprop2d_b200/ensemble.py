@@ -96,8 +96,10 @@ class EnsemblePropagator:
         torch = _torch()
         return C.c_void_p(torch.cuda.current_stream(self._tdev).cuda_stream)
 
-    def intensity(self, fields, z, out=None):
-        """|ifft2(fft2(fields) * H(z))|^2 for device ``fields`` of shape (B, N, N); returns a device tensor."""
+    def intensity(self, fields, z, out=None, work=None):
+        """|ifft2(fft2(fields) * H(z))|^2 for device ``fields`` of shape (B, N, N); returns a device tensor.
+        ``work``: scratch for the intermediates (default: the propagator's own buffer; callers that run
+        several calls concurrently on different streams pass one buffer per stream)."""
         torch = _torch()
         if fields.dtype != self._cdtype or not fields.is_cuda:
             raise ValueError(f"fields must be a CUDA tensor of dtype {self._cdtype}")
@@ -110,7 +112,8 @@ class EnsemblePropagator:
             out = torch.empty(fields.shape, dtype=self._rdtype, device=self._tdev)
         with torch.cuda.device(self._tdev):
             _lib.check(self._lib.lp2d_propagate_field(self._plan.handle, fields.data_ptr(), None, None,
-                                                      out.data_ptr(), self._work.data_ptr(), self._work.numel(),
+                                                      out.data_ptr(), (self._work if work is None else work).data_ptr(),
+                                                      (self._work if work is None else work).numel(),
                                                       batch, float(z), self._stream()), "propagate_field")
         return out
 
@@ -131,26 +134,36 @@ class EnsemblePropagator:
     def intensity_from_host(self, host_fields, z, chunk=16, out=None):
         """End-to-end form: ``host_fields`` is a pinned (or pageable) CPU tensor / numpy array of
         shape (B, N, N); every chunk is copied H2D, propagated and its intensity copied D2H, with the
-        copies of neighbouring chunks overlapped on two streams.  Returns a pinned CPU tensor."""
+        copies of neighbouring chunks overlapped on three streams.  Returns a pinned CPU tensor."""
         torch = _torch()
         if isinstance(host_fields, np.ndarray):
             host_fields = torch.from_numpy(host_fields)
         B = host_fields.shape[0]
         if out is None:
             out = torch.empty(host_fields.shape, dtype=self._rdtype, pin_memory=True)
-        streams = [torch.cuda.Stream(self._tdev), torch.cuda.Stream(self._tdev)]
-        dev_in = [torch.empty((chunk,) + tuple(host_fields.shape[1:]), dtype=self._cdtype, device=self._tdev) for _ in range(2)]
-        dev_out = [torch.empty((chunk,) + tuple(host_fields.shape[1:]), dtype=self._rdtype, device=self._tdev) for _ in range(2)]
+        # streams and staging buffers are kept between calls (per chunk shape)
+        key = (chunk,) + tuple(host_fields.shape[1:])
+        cache = getattr(self, "_e2e_cache", None)
+        if cache is None or cache[0] != key:
+            nbuf = 3
+            cache = (key,
+                     [torch.cuda.Stream(self._tdev) for _ in range(nbuf)],
+                     [torch.empty((chunk,) + tuple(host_fields.shape[1:]), dtype=self._cdtype, device=self._tdev) for _ in range(nbuf)],
+                     [torch.empty((chunk,) + tuple(host_fields.shape[1:]), dtype=self._rdtype, device=self._tdev) for _ in range(nbuf)],
+                     [torch.empty_like(self._work) for _ in range(nbuf)])      # one scratch buffer per stream
+            self._e2e_cache = cache
+        _, streams, dev_in, dev_out, works = cache
+        nbuf = len(streams)
         cur = torch.cuda.current_stream(self._tdev)
         for s in streams:
             s.wait_stream(cur)
         for k, b0 in enumerate(range(0, B, chunk)):
             nb = min(chunk, B - b0)
-            s = streams[k % 2]
+            s = streams[k % nbuf]
             with torch.cuda.stream(s):
-                dev_in[k % 2][:nb].copy_(host_fields[b0:b0 + nb], non_blocking=True)
-                self.intensity(dev_in[k % 2][:nb], z, out=dev_out[k % 2][:nb])
-                out[b0:b0 + nb].copy_(dev_out[k % 2][:nb], non_blocking=True)
+                dev_in[k % nbuf][:nb].copy_(host_fields[b0:b0 + nb], non_blocking=True)
+                self.intensity(dev_in[k % nbuf][:nb], z, out=dev_out[k % nbuf][:nb], work=works[k % nbuf])
+                out[b0:b0 + nb].copy_(dev_out[k % nbuf][:nb], non_blocking=True)
         for s in streams:
             cur.wait_stream(s)
         return out

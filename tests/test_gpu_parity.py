@@ -310,7 +310,7 @@ def test_config3_ensemble_subset_parity():
     prop = EnsemblePropagator(area, n, wl, complex_bits=64)
     dev = torch.from_numpy(fields).cuda()
     got = prop.intensity(dev, z).cpu().numpy()
-    got_e2e = prop.intensity_from_host(torch.from_numpy(fields).pin_memory(), z, chunk=24)
+    got_e2e = prop.intensity_from_host(torch.from_numpy(fields).pin_memory(), z, chunk=8)   # 8 chunks over 3 streams
     torch.cuda.synchronize()
     fld = prop.field(dev, z).cpu().numpy()
     for k in range(0, B, 7):
