@@ -70,8 +70,9 @@ struct lp2d_plan {
     void* p2_fac;              // factor plane [n][fl]
     int fac_kind, fac_by_column;   // what p2_fac currently holds (0 = nothing)
     double fac_p0, fac_p1;
-    cudaEvent_t p2_done;       // end of the last fused launch: the ring, the counters and the factor plane are
-                               // plan state, so fused launches of one plan are serialised across streams
+    cudaEvent_t p2_done;       // the ring, the counters and the factor plane are plan state: fused launches of one
+    cudaStream_t p2_stream;    // plan are serialised across streams (event recorded on the old stream at a switch)
+    bool p2_used;
 };
 
 #define LP2D_CHECK_PLAN(p)                                                      \
@@ -179,7 +180,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         return cuda_fail(e, "cudaMemcpy(tables)");
     }
     p->ring = nullptr; p->counters = nullptr; p->ring_bytes = 0; p->counters_cap = 0; p->num_sms = 0;
-    p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr;
+    p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
     if (env == nullptr || atoi(env) == 2) {
@@ -198,7 +199,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
             p->counters_cap = 1 + P2_MAX_STAGES * 16384;
             if (e == cudaSuccess) e = cudaMalloc(&p->ring, (size_t)ring_bytes);
-            if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * p->counters_cap);
+            if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * (p->counters_cap + 1));
+            // zeroed once: every launch leaves the counters it used zeroed (t3_kernel)
+            if (e == cudaSuccess) e = cudaMemset(p->counters, 0, sizeof(unsigned int) * (p->counters_cap + 1));
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_tw, n2 * csz);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_fac, (size_t)n * (q32 ? q32->fl : q64->fl) * csz);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->p2_done, cudaEventDisableTiming);
@@ -344,8 +347,17 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     if (p->pipe_slots > 0) slots = p->pipe_slots > (nstages - 1) * lag + 1 ? p->pipe_slots : (nstages - 1) * lag + 1;
     while (G > 1 && slots * G * plane > p->ring_bytes) --G;
     if (slots * G * plane > p->ring_bytes) return -1;
-    // wait for the previous fused launch of this plan, whichever stream it ran on
-    LP2D_CU(cudaStreamWaitEvent(s, p->p2_done, 0), "fused step: wait for the previous launch");
+    // launches on one stream are ordered anyway; when the caller switches streams, the new stream waits for
+    // everything queued so far on the old one (which includes the previous fused launch of this plan)
+    if (p->p2_used && p->p2_stream != s) {
+        if (cudaEventRecord(p->p2_done, p->p2_stream) == cudaSuccess) {
+            LP2D_CU(cudaStreamWaitEvent(s, p->p2_done, 0), "fused step: wait for the previous stream");
+        } else {
+            cudaGetLastError();                     // the previous stream no longer exists: wait for the device
+            LP2D_CU(cudaDeviceSynchronize(), "fused step: device synchronise");
+        }
+    }
+    p->p2_stream = s; p->p2_used = true;
     if (need_factor) {
         const int rc = p2_ensure_factor<T>(p, fac_kind, by_column, p0, p1, s);
         if (rc) return rc;
@@ -380,11 +392,9 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         const long long total = ((long long)a.ngroups + (long long)(nstages - 1) * lag) * nstages * tiles;
         if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "fused step: batch too large for one launch");
         a.total_items = (int)total;
-        LP2D_CU(cudaMemsetAsync(p->counters, 0, sizeof(unsigned int) * (1 + (size_t)nstages * a.ngroups), s), "fused step counters");
         const unsigned grid = (unsigned)total;      // one CTA per item
         LP2D_CU(ops->launch(a, grid, need_factor, s, p->ring, p->pipe_persist ? (size_t)(slots * G * plane) : 0), "fused step launch");
     }
-    LP2D_CU(cudaEventRecord(p->p2_done, s), "fused step: record completion");
     return LP2D_OK;
 }
 

@@ -61,7 +61,7 @@ struct P2Args {
     cx<T>* ring;              // ring_slots * G planes
     const cx<T>* tw;          // twiddles of LinePlan<N, E>
     const cx<T>* fac;         // factor plane [N lines][FL], folded (P2_MAP_*)
-    unsigned int* counters;   // [0] next item; [1 + s*ngroups + g] completed items of (s, g)
+    unsigned int* counters;   // [0] next item; [1 + s*ngroups + g] completed items of (s, g); then CTAs that have exited
     long long nbeams;
     int nstages, ngroups, G, lag, ring_slots, total_items, fac_map;
     int hints;                // P2_HINT_*
@@ -81,7 +81,7 @@ __device__ __forceinline__ void p2_signal(unsigned int* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
-enum { P2_HINT_STREAM_IN = 1, P2_HINT_KEEP_RING = 2, P2_HINT_STREAM_OUT = 4, P2_HINT_BLOCK_TICKET = 8 };
+enum { P2_HINT_STREAM_IN = 1, P2_HINT_KEEP_RING = 2 };
 // KIND is a compile-time value: a policy selected at run time ends up in a misaligned uniform
 // register pair (ptxas 12.9) and the copy traps as an illegal instruction.
 template <int KIND>     // 0 no hint, 1 evict first, 2 evict last
@@ -304,50 +304,46 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     __shared__ int s_item;
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
-    // P2_HINT_BLOCK_TICKET: the item number is the block index (CTAs are dispatched in block-index
-    // order), every warp waits for the dependencies and signals completion on its own: no ticket
-    // round trip and no CTA barrier outside the transforms.  Otherwise thread 0 draws a ticket.
-    const bool block_ticket = (p.hints & P2_HINT_BLOCK_TICKET) != 0;
-    int item;
-    if (block_ticket) {
-        item = (int)blockIdx.x;
+    if (tid == 0) {
+        const int drawn = (int)atomicAdd(&p.counters[0], 1u);
         P2Item it0;
-        if (item >= p.total_items || !p2_decode<T, K::TILES>(p, item, it0)) return;
-        if ((tid & 31) == 0) p2_wait_ready<T, K::TILES>(p, item, (unsigned)K::TILES * (K::THREADS / 32));
-        __syncwarp();
-    } else {
-        if (tid == 0) {
-            const int drawn = (int)atomicAdd(&p.counters[0], 1u);
-            P2Item it0;
-            if (drawn < p.total_items && p2_decode<T, K::TILES>(p, drawn, it0)) {
-                p2_wait_ready<T, K::TILES>(p, drawn, (unsigned)K::TILES);
-                s_item = drawn;
-            } else {
-                s_item = -1;
-            }
+        if (drawn < p.total_items && p2_decode<T, K::TILES>(p, drawn, it0)) {
+            p2_wait_ready<T, K::TILES>(p, drawn, (unsigned)K::TILES);
+            s_item = drawn;
+        } else {
+            s_item = -1;                                   // fill / drain item of the schedule: nothing to do
         }
-        __syncthreads();
-        item = s_item;
-        if (item < 0) return;
     }
-    P2Item it;
-    p2_decode<T, K::TILES>(p, item, it);
-    if (it.s == 0) {
-        if (p.st[0].inverse) t3_item<T, N, E, W, 0, AX_ROW, false, true, false, true>(p, it, xbuf, tid);
-        else t3_item<T, N, E, W, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
-    } else if (it.s == 1) {
-        if (p.st[1].mid) t3_item<T, N, E, W, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
-        else if (p.st[1].inverse) t3_item<T, N, E, W, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
-        else t3_item<T, N, E, W, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
-    } else {
-        t3_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
-    }
-    if (block_ticket) {
-        __syncwarp();                                      // this warp's stores are issued
-        if ((tid & 31) == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
-    } else {
+    __syncthreads();
+    const int item = s_item;
+    if (item >= 0) {
+        P2Item it;
+        p2_decode<T, K::TILES>(p, item, it);
+        if (it.s == 0) {
+            if (p.st[0].inverse) t3_item<T, N, E, W, 0, AX_ROW, false, true, false, true>(p, it, xbuf, tid);
+            else t3_item<T, N, E, W, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
+        } else if (it.s == 1) {
+            if (p.st[1].mid) t3_item<T, N, E, W, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
+            else if (p.st[1].inverse) t3_item<T, N, E, W, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
+            else t3_item<T, N, E, W, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
+        } else {
+            t3_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
+        }
         __syncthreads();                                   // all stores of the item are issued
         if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+    }
+    // The CTA that finishes last leaves the counters zeroed for the next launch (no memset per step):
+    // every CTA counts itself out after its last access to the counters; whoever brings the count to the
+    // grid size knows that nobody reads them any more.
+    if (tid == 0) {
+        const unsigned int ncnt = 1u + (unsigned)p.nstages * (unsigned)p.ngroups;       // index of the exit counter
+        __threadfence();
+        s_item = (atomicAdd(&p.counters[ncnt], 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_item) {
+        const unsigned int ncnt = 1u + (unsigned)p.nstages * (unsigned)p.ngroups;
+        for (unsigned int i = tid; i <= ncnt; i += K::THREADS) p.counters[i] = 0u;
     }
 }
 
