@@ -148,6 +148,16 @@ LP2D_API int lp2d_expand(int dtype, const void* in, void* out, int n_in, int n_o
 LP2D_API int lp2d_coarse(int dtype, const void* in, void* out, int n_in, int m, long long batch,
                 void* stream);
 
+/* Ensemble inputs generated on the device: `batch` fields of
+ * profiles.random_round_hole (kind 0: amplitude uniform in [0,1) inside the aperture, profiles.py:94-101)
+ * or profiles.random_round_hole_phase (kind 1: exp(2 pi i u) inside, profiles.py:104-113), zero outside.
+ * `mask_u8` (device, n*n bytes) is the host-built profiles.round_hole array, so the aperture is exactly
+ * the reference's.  The uniform numbers come from a counter-based generator (Philox4x32-10) keyed by
+ * (seed, first_beam + b, sample index): a beam does not depend on the batch or the rank it is generated in
+ * (the numpy stream of the reference cannot be reproduced on the device; parity tests use host inputs). */
+LP2D_API int lp2d_random_fields(int dtype, void* out, const void* mask_u8, int n, long long batch,
+                       unsigned long long first_beam, unsigned long long seed, int kind, void* stream);
+
 /* phiprofile (beam2d.py:734): out = atan2(im, re) for `count` samples. */
 LP2D_API int lp2d_phase(int dtype, const void* field, void* out, long long count, void* stream);
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "lp2d_intensity": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "lp2d_expand": (_i, [_i, _vp, _vp, _i, _i, _ll, _vp]),
     "lp2d_coarse": (_i, [_i, _vp, _vp, _i, _i, _ll, _vp]),
+    "lp2d_random_fields": (_i, [_i, _vp, _vp, _i, _ll, C.c_ulonglong, C.c_ulonglong, _i, _vp]),
     "lp2d_phase": (_i, [_i, _vp, _vp, _ll, _vp]),
     "lp2d_moments": (_i, [_i, _vp, _i, _d, _d, _d, _vp, _vp]),
     "lp2d_modes_project": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),

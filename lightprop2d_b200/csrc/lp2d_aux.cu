@@ -49,6 +49,69 @@ __global__ void pack_transpose_kernel(const cx<T>* __restrict__ in, cx<T>* __res
     }
 }
 
+// Counter-based RNG (Philox4x32-10, Salmon et al. 2011) for ensembles generated on the device: the four
+// words of block `ctr` of beam `beam` depend only on (seed, beam, ctr), so a beam is the same whatever the
+// batch / shard it is generated in.
+__device__ __forceinline__ void philox4x32_10(unsigned int (&c)[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const unsigned int n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// random_round_hole (kind 0: amplitude uniform in [0,1) inside the aperture) / random_round_hole_phase
+// (kind 1: exp(2 pi i u) inside the aperture), zero outside (profiles.py:94-113); the aperture mask is the
+// host-built round_hole array (exactly the reference's comparison), one byte per grid point.
+template <typename T>
+__global__ void random_fields_kernel(cx<T>* __restrict__ out, const unsigned char* __restrict__ mask, long long plane,
+                                     long long batch, unsigned long long first_beam, unsigned long long seed, int kind) {
+    const long long quads = (plane + 3) / 4;
+    const long long total = quads * batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / quads, q = i - b * quads;
+        const unsigned long long beam = first_beam + (unsigned long long)b;
+        unsigned int c[4] = {(unsigned int)q, (unsigned int)((unsigned long long)q >> 32), (unsigned int)beam, (unsigned int)(beam >> 32)};
+        if (sizeof(T) == 8) {
+            // two 32-bit words per sample: two Philox blocks per quad
+            unsigned int d[4] = {c[0], c[1] | 0x80000000u, c[2], c[3]};
+            philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+            philox4x32_10(d, (unsigned int)seed, (unsigned int)(seed >> 32));
+            const unsigned int w[8] = {c[0], c[1], c[2], c[3], d[0], d[1], d[2], d[3]};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long idx = q * 4 + j;
+                if (idx >= plane) break;
+                const unsigned long long bits = ((unsigned long long)w[2 * j] << 21) ^ (unsigned long long)(w[2 * j + 1] >> 11);   // 53 bits
+                const double u = (double)(bits & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+                cx<T> v = mk<T>((T)0, (T)0);
+                if (mask[idx]) {
+                    if (kind == 0) v = mk<T>((T)u, (T)0);
+                    else { double sn, cs; sincospi(2.0 * u, &sn, &cs); v = mk<T>((T)cs, (T)sn); }
+                }
+                out[b * plane + idx] = v;
+            }
+        } else {
+            philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long idx = q * 4 + j;
+                if (idx >= plane) break;
+                const float u = (float)(c[j] >> 8) * (1.0f / 16777216.0f);                // 24 bits, [0, 1)
+                cx<T> v = mk<T>((T)0, (T)0);
+                if (mask[idx]) {
+                    if (kind == 0) v = mk<T>((T)u, (T)0);
+                    else { float sn, cs; sincospif(2.0f * u, &sn, &cs); v = mk<T>((T)cs, (T)sn); }
+                }
+                out[b * plane + idx] = v;
+            }
+        }
+    }
+}
+
 // out[b][r][c] = mean of the m x m block                  (beam2d.py:456-459)
 template <typename T>
 __global__ void coarse_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int n_in, int m,
@@ -227,6 +290,21 @@ int lp2d_pack_transpose(int dtype, const void* in, void* out, int rows, int ld, 
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("pack_transpose launch: ") + cudaGetErrorString(e));
     return LP2D_OK;
+}
+
+int lp2d_random_fields(int dtype, void* out, const void* mask_u8, int n, long long batch, unsigned long long first_beam,
+                       unsigned long long seed, int kind, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || out == nullptr || mask_u8 == nullptr || n <= 0 || batch < 0 || (kind != 0 && kind != 1))
+        return set_error(LP2D_EINVAL, "random_fields: bad arguments");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long plane = (long long)n * n;
+    const unsigned grid = grid_for(((plane + 3) / 4) * batch, 256);
+    if (dtype == LP2D_C64)
+        random_fields_kernel<float><<<grid, 256, 0, s>>>(static_cast<float2*>(out), static_cast<const unsigned char*>(mask_u8), plane, batch, first_beam, seed, kind);
+    else
+        random_fields_kernel<double><<<grid, 256, 0, s>>>(static_cast<double2*>(out), static_cast<const unsigned char*>(mask_u8), plane, batch, first_beam, seed, kind);
+    return done("random_fields launch");
 }
 
 int lp2d_coarse(int dtype, const void* in, void* out, int n_in, int m, long long batch, void* stream) {

@@ -96,6 +96,32 @@ class EnsemblePropagator:
         torch = _torch()
         return C.c_void_p(torch.cuda.current_stream(self._tdev).cuda_stream)
 
+    def random_fields(self, batch, R, x0=0., y0=0., seed=0, first_beam=0, phase=False, out=None):
+        """``batch`` input fields generated on the device: ``profiles.random_round_hole`` (``phase=False``:
+        amplitude uniform in [0, 1) inside the aperture) or ``profiles.random_round_hole_phase``
+        (``phase=True``: exp(2 pi i u) inside), zero outside (profiles.py:94-113).  The aperture is the
+        host-built ``round_hole(X, Y, R, x0, y0)`` array -- exactly the reference's -- uploaded once; the
+        uniform numbers come from a counter-based generator keyed by (seed, first_beam + b, sample), so
+        beam ``first_beam + b`` is the same whatever batch or rank generates it (shard with
+        ``shard_range`` and pass the block start as ``first_beam``)."""
+        torch = _torch()
+        from . import profiles
+        key = (float(R), float(x0), float(y0))
+        if getattr(self, "_mask_key", None) != key:
+            dL = self.area_size / self.npoints
+            X = np.arange(-self.npoints // 2, self.npoints // 2, 1) * dL
+            m = profiles.round_hole(X.copy(), X.reshape((-1, 1)).copy(), R, x0, y0)
+            self._mask_dev = torch.from_numpy(np.ascontiguousarray(m.astype(np.uint8))).to(self._tdev)
+            self._mask_key = key
+        n = self.npoints
+        if out is None:
+            out = torch.empty((int(batch), n, n), dtype=self._cdtype, device=self._tdev)
+        with torch.cuda.device(self._tdev):
+            _lib.check(self._lib.lp2d_random_fields(_lib.C64 if self.complex_bits == 64 else _lib.C128, out.data_ptr(),
+                                                    self._mask_dev.data_ptr(), n, int(batch), int(first_beam), int(seed),
+                                                    1 if phase else 0, self._stream()), "random_fields")
+        return out
+
     def intensity(self, fields, z, out=None, work=None):
         """|ifft2(fft2(fields) * H(z))|^2 for device ``fields`` of shape (B, N, N); returns a device tensor.
         ``work``: scratch for the intermediates (default: the propagator's own buffer; callers that run

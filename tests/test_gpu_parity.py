@@ -495,3 +495,46 @@ def test_fused_step_equals_per_pass_kernels():
         assert rel_l2(res[("2", nb)][0], res[("0", nb)][0]) <= 2e-6
         assert rel_l2(res[("2", nb)][1], res[("0", nb)][1]) <= 2e-6
     torch.cuda.synchronize()
+
+
+# ----------------------------------------------------------------------------- device-side ensemble inputs
+def _philox4x32_10(ctr, key):
+    """Reference implementation (Salmon et al. 2011) for the known-answer checks below."""
+    c = list(ctr); k = list(key)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+@pytest.mark.gpu
+def test_device_generated_ensemble_inputs():
+    """EnsemblePropagator.random_fields: aperture identical to profiles.round_hole, counter-based numbers
+    (bit-exact against a host Philox4x32-10), beams independent of the batch / shard they are generated in."""
+    assert _philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]   # published KAT
+    n, area, R = 256, 400 * um, 150 * um
+    prop = EnsemblePropagator(area, n, 632 * nm, complex_bits=64)
+    f = prop.random_fields(16, R, seed=1234).cpu().numpy()
+    X = np.arange(-n // 2, n // 2) * (area / n)
+    hole = lp.round_hole(X.copy(), X.reshape(-1, 1).copy(), R)
+    assert np.all(f[:, ~hole] == 0) and np.all(f.imag == 0)
+    inside = f.real[:, hole]
+    assert inside.min() >= 0 and inside.max() < 1 and abs(inside.mean() - 0.5) < 5e-3
+    # bit-exact numbers: beam 3, samples 8..11 are the four words of block 2
+    w = _philox4x32_10([2, 0, 3, 0], [1234, 0])
+    exp = np.array([(x >> 8) / 16777216.0 for x in w], dtype=np.float32) * hole.ravel()[8:12]
+    assert np.array_equal(f[3].real.ravel()[8:12], exp)
+    # shard invariance: beams 5..8 generated on their own
+    g = prop.random_fields(4, R, seed=1234, first_beam=5).cpu().numpy()
+    assert np.array_equal(g, f[5:9])
+    assert not np.array_equal(prop.random_fields(1, R, seed=1235).cpu().numpy()[0], f[0])
+    # phase kind: unit modulus inside, complex128 too
+    ph = prop.random_fields(2, R, seed=7, phase=True).cpu().numpy()
+    assert np.allclose(np.abs(ph[:, hole]), 1, atol=1e-6) and np.all(ph[:, ~hole] == 0)
+    p128 = EnsemblePropagator(area, n, 632 * nm, complex_bits=128)
+    d = p128.random_fields(2, R, seed=7).cpu().numpy()
+    assert d.dtype == np.complex128 and d.real[:, hole].max() < 1 and np.all(d[:, ~hole] == 0)
+    # and they propagate: energy conserved
+    I = prop.intensity(prop.random_fields(4, R, seed=9, phase=True), 100 * um).cpu().numpy()
+    assert np.allclose(I.sum((1, 2)), hole.sum(), rtol=1e-4)
