@@ -23,6 +23,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef LP2D_TWO_LEVEL_TWIDDLES
+#define LP2D_TWO_LEVEL_TWIDDLES 0
+#endif
+
 namespace lp2d {
 
 template <typename T> struct Cx2;
@@ -217,7 +221,21 @@ __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sli
         for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
         if (Ns > 1) {
             const int k = j & (Ns - 1);
-            if constexpr (R > 16) {
+            if constexpr (R > 16 && sizeof(T) == 4 && LP2D_TWO_LEVEL_TWIDDLES) {
+                // radix 32, FP32: w^(k r) = w^(4a k) * w^(b k) with r = 4a + b: 10 table loads (b = 1..3,
+                // 4a = 4..28) instead of 31, 52 complex multiplies instead of 31 -- the L1 data pipe, not
+                // the FP pipe, is the scarce resource of the fused kernel
+                cx<T> wb[3], wa[7];
+#pragma unroll
+                for (int b = 1; b < 4; ++b) wb[b - 1] = __ldg(&tw[twoff + (b - 1) * Ns + k]);
+#pragma unroll
+                for (int a = 1; a < 8; ++a) wa[a - 1] = __ldg(&tw[twoff + (4 * a - 1) * Ns + k]);
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    if ((r >> 2) > 0) u[r] = cmul(u[r], wa[(r >> 2) - 1]);
+                    if ((r & 3) > 0) u[r] = cmul(u[r], wb[(r & 3) - 1]);
+                }
+            } else if constexpr (R > 16) {
                 // radix 32: 31 twiddle loads hoisted above their uses would need 62 registers on top of
                 // the 64 of the data (spills at 128 registers): load and apply them eight at a time
 #pragma unroll

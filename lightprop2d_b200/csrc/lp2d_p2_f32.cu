@@ -1,5 +1,8 @@
 // complex64 instances of the fused step kernel: (N, E, lines per CTA, min CTAs/SM)
 #define LP2D_PACKED_F32 1
+#ifndef LP2D_TWO_LEVEL_TWIDDLES
+#define LP2D_TWO_LEVEL_TWIDDLES 1
+#endif
 #include "pipe2_ops.cuh"
 
 namespace lp2d {
