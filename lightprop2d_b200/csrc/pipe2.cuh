@@ -27,6 +27,8 @@
 // cp.async staging, staged tile groups, an E = 16 body at 64 registers, block-index tickets, an L2
 // persisting window): DESIGN.md section 5 and profiles/r1b_*, r1c_*; the code is in the git history.
 #pragma once
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched from the driver at run time)
+#include <cstdint>
 #include "kernels.cuh"
 
 namespace lp2d {
@@ -65,6 +67,11 @@ struct P2Args {
     long long nbeams;
     int nstages, ngroups, G, lag, ring_slots, total_items, fac_map;
     int hints;                // P2_HINT_*
+    // TMA path of the final column stage of two-stage steps (use_tma != 0): 2-D tensor maps over the ring
+    // and over the output planes, seen as [plane * N + row][N * sizeof(complex) / 4 floats]
+    int use_tma;
+    alignas(64) CUtensorMap tm_ring;
+    alignas(64) CUtensorMap tm_out;
 };
 
 __device__ __forceinline__ unsigned int p2_ld_relaxed(const unsigned int* ctr) {
@@ -297,14 +304,124 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// TMA form of the final column stage (ring -> user planes) of two-stage steps.  A column tile is N
+// rows of W * sizeof(complex) bytes: per-thread loads / stores touch one 128-byte line per 64 bytes
+// (twice the L1 wavefronts of a row access); here the tile is fetched and written back by the TMA unit
+// as boxes of 256 rows (cp.async.bulk.tensor.2d), the threads only see shared memory.
+__device__ __forceinline__ uint32_t p2_smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void p2_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p2_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void p2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void p2_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = p2_smem_u32(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000ll) __trap();      // never hang the device on a lost copy
+    }
+}
+__device__ __forceinline__ void p2_tma_load_2d(void* smem_dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     p2_smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(p2_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void p2_tma_store_2d(const CUtensorMap* tm, int x, int y, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(x), "r"(y), "r"(p2_smem_u32(smem_src))
+                 : "memory");
+}
+
+template <typename T, int N, int E, int W, bool INV>
+__device__ __forceinline__ void t3_col_tma_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, uint64_t* bar, uint32_t& parity,
+                                                int tid) {
+    using K = T3Cfg<T, N, E, W>;
+    constexpr int TPL = K::TPL;
+    constexpr long long PLANE = (long long)N * N;
+    constexpr int BOX = (N < 256) ? N : 256;                   // rows per TMA box
+    constexpr int FPC = (int)sizeof(cx<T>) / 4;                // floats per complex sample (tensor maps are in floats)
+    const P2Stage<T>& st = p.st[1];
+    const int l = tid % W, t = tid / W;
+    cx<T>* sline = xbuf + l * K::LS;
+    const long long b0 = (long long)it.g * p.G;
+    const long long slot0 = (long long)(it.g % p.ring_slots) * p.G;
+    const long long left = p.nbeams - b0;
+    const int nb = left < p.G ? (int)left : p.G;
+    const int col0 = it.tile * W;
+
+    for (int bi = 0; bi < nb; ++bi) {
+        const long long b = b0 + bi;
+        if (tid == 0) {
+            p2_mbar_expect_tx(bar, (uint32_t)(N * W * sizeof(cx<T>)));
+#pragma unroll
+            for (int k = 0; k < N / BOX; ++k)
+                p2_tma_load_2d(xbuf + (long long)k * BOX * W, &p.tm_ring, col0 * FPC, (int)((slot0 + bi) * N) + k * BOX, bar);
+        }
+        p2_mbar_wait(bar, parity);
+        parity ^= 1u;
+        cx<T> v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = xbuf[(t + TPL * m) * W + l];
+        line_fft<T, N, E, SYNC_CTA>(v, sline, p.tw, t, l);     // the first pass synchronises before it scatters
+        if (st.scale != (T)1) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cscale(v[m], st.scale);
+        }
+        __syncthreads();                                       // every thread has done its last gather
+        // results -> shared memory in the plane's orientation [row][W]; inverse = mirrored row index
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int pos = t + TPL * m;
+            xbuf[(INV ? ((N - pos) & (N - 1)) : pos) * W + l] = v[m];
+        }
+        if (st.inten != nullptr) {
+            T* dst = st.inten + b * PLANE + col0 + l;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int pos = t + TPL * m;
+                __stcs(dst + (long long)(INV ? ((N - pos) & (N - 1)) : pos) * N, v[m].x * v[m].x + v[m].y * v[m].y);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < N / BOX; ++k)
+                p2_tma_store_2d(&p.tm_out, col0 * FPC, (int)(b * N) + k * BOX, xbuf + (long long)k * BOX * W);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile has been read out of shared memory
+        }
+        __syncthreads();
+    }
+    // the completion signal of this (final) stage only says that the ring slot has been consumed; the
+    // bulk stores complete before the grid does
+}
+
 template <typename T, int N, int E, int W, int MINB>
 __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(const __grid_constant__ P2Args<T> p) {
     using K = T3Cfg<T, N, E, W>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_item;
+    __shared__ uint64_t s_bar;                             // TMA loads of the column stage
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
+    uint32_t tma_parity = 0;
     if (tid == 0) {
+        if (p.use_tma) p2_mbar_init(&s_bar, 1);
         const int drawn = (int)atomicAdd(&p.counters[0], 1u);
         P2Item it0;
         if (drawn < p.total_items && p2_decode<T, K::TILES>(p, drawn, it0)) {
@@ -324,6 +441,8 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
             else t3_item<T, N, E, W, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
         } else if (it.s == 1) {
             if (p.st[1].mid) t3_item<T, N, E, W, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
+            else if (p.use_tma && p.st[1].inverse) t3_col_tma_item<T, N, E, W, true>(p, it, xbuf, &s_bar, tma_parity, tid);
+            else if (p.use_tma) t3_col_tma_item<T, N, E, W, false>(p, it, xbuf, &s_bar, tma_parity, tid);
             else if (p.st[1].inverse) t3_item<T, N, E, W, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
             else t3_item<T, N, E, W, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
         } else {

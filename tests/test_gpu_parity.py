@@ -538,3 +538,44 @@ def test_device_generated_ensemble_inputs():
     # and they propagate: energy conserved
     I = prop.intensity(prop.random_fields(4, R, seed=9, phase=True), 100 * um).cpu().numpy()
     assert np.allclose(I.sum((1, 2)), hole.sum(), rtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_fused_step_tma_column_stage():
+    """LP2D_TMA=1: the final column stage of the fused step through cp.async.bulk.tensor (ring -> shared
+    memory -> output planes) gives the same field as per-thread accesses, bit for bit, with and without the
+    fused |E|^2 output, for a ragged batch."""
+    import ctypes as C
+    import os
+    import torch
+    from lightprop2d_b200 import beam2d as _b
+    from lightprop2d_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    f0 = (rng.standard_normal((3, 1024, 1024)) + 1j * rng.standard_normal((3, 1024, 1024))).astype(np.complex64)
+    res = {}
+    old = os.environ.get("LP2D_TMA")
+    try:
+        for mode in ("0", "1"):
+            os.environ["LP2D_TMA"] = mode
+            _b._PLAN_CACHE.clear()
+            b = Beam2D(4e-1, 1024, 532e-7, init_field=f0.copy(), complex_bits=64, use_gpu=True, numpy_output=False)
+            b.propagate(0.02)
+            b.propagate(-0.013)
+            inten = torch.empty(3, 1024, 1024, dtype=torch.float32, device="cuda")
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            L.check(L.load().lp2d_propagate(b._plan.handle, b._s.data_ptr(), b._f.data_ptr(), inten.data_ptr(), 3, 0.5, st))
+            torch.cuda.synchronize()
+            res[mode] = (b._f.cpu().numpy().copy(), b._s.cpu().numpy().copy(), inten.cpu().numpy().copy())
+    finally:
+        if old is None:
+            os.environ.pop("LP2D_TMA", None)
+        else:
+            os.environ["LP2D_TMA"] = old
+        _b._PLAN_CACHE.clear()
+    for k in range(3):
+        assert np.array_equal(res["0"][k], res["1"][k])
+    o = orc.OracleBeam(4e-1, 1024, 532e-7, init_field=f0.copy(), complex_bits=64)
+    for z in (0.02, -0.013, 0.5):
+        o.propagate(z)
+    assert rel_l2(res["1"][0], o.field) <= TOL[64]
+    assert rel_l2(res["1"][2], o.iprofile) <= TOL[64]
