@@ -89,7 +89,7 @@ struct lp2d_plan {
     long long ring_bytes;
     unsigned int* counters;    // work queue head + per-(stage, group) completion counters
     int counters_cap;
-    int pipe_g, pipe_lag, pipe_slots, pipe_grid;   // tuning overrides (0 = automatic)
+    int pipe_g, pipe_lag, pipe_slots;   // tuning overrides (0 = automatic)
     int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
     int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
     int use_tma;               // final column stage of two-stage fused steps through the TMA unit
@@ -257,7 +257,6 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_LAG");   p->pipe_lag = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_SLOTS"); p->pipe_slots = env ? atoi(env) : 0;
-    env = getenv("LP2D_PIPE_GRID");  p->pipe_grid = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_HINTS"); p->pipe_hints = env ? atoi(env) : 3;
     // measured (profiles/r1c_size_sweep.log): the fused kernel wins on the steps that read AND write state
     // (3*P*B algorithmic bytes); plain fft2 and the three-stage fresh chain stay on the per-pass kernels
@@ -365,7 +364,6 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
     const int ctas = need_factor ? p->p2_ctas_factor : p->p2_ctas_plain;
     long long conc = (long long)ctas * p->num_sms;
-    if (p->pipe_grid > 0 && p->pipe_grid < conc) conc = p->pipe_grid;
     const int tiles = ops->tiles;
     // beams per work item: two for planes of up to 512 points (halves the per-item overhead; the ring still
     // fits L2), one for 1024 points (the ring would double to 64 MB)

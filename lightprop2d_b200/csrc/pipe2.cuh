@@ -79,16 +79,11 @@ __device__ __forceinline__ unsigned int p2_ld_relaxed(const unsigned int* ctr) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr));
     return v;
 }
-__device__ __forceinline__ unsigned int p2_ld_acquire(const unsigned int* ctr) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    return v;
-}
 __device__ __forceinline__ void p2_signal(unsigned int* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
-enum { P2_HINT_STREAM_IN = 1, P2_HINT_KEEP_RING = 2 };
+enum { P2_HINT_KEEP_RING = 2 };      // bit 0 was the (dropped) hint on the cp.async path
 // KIND is a compile-time value: a policy selected at run time ends up in a misaligned uniform
 // register pair (ptxas 12.9) and the copy traps as an illegal instruction.
 template <int KIND>     // 0 no hint, 1 evict first, 2 evict last
