@@ -9,10 +9,14 @@ static const SizeOps<double> kOpsF64[] = {
     Ops<double, 128, 8, 8, 8>::entry(),
     Ops<double, 256, 8, 8, 8>::entry(),
     Ops<double, 512, 8, 4, 4>::entry(),
-    Ops<double, 1024, 8, 2, 4>::entry(),
-    Ops<double, 1024, 8, 2, 8>::entry(1),
+    // 1024: E = 16 (two exchanges instead of three): fresh chain +16 %, stateful +3 % (profiles/r1c_large_n_variants.log)
+    Ops<double, 1024, 16, 2, 4>::entry(),
+    Ops<double, 1024, 8, 2, 4>::entry(1),
+    Ops<double, 1024, 8, 2, 8>::entry(2),
     Ops<double, 2048, 8, 1, 2>::entry(),
     Ops<double, 2048, 8, 1, 4>::entry(1),
+    Ops<double, 2048, 16, 2, 4>::entry(2),
+    Ops<double, 2048, 16, 1, 2>::entry(3),
     Ops<double, 4096, 8, 1, 2>::entry(),
     Ops<double, 4096, 8, 1, 1>::entry(1),
 };
