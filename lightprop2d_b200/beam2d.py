@@ -431,7 +431,19 @@ class Beam2D:
         return self.modes_coeffs
 
     def fast_deconstruct_by_modes(self, modes_matrix_t, modes_matrix_dot_t):
-        raise NotImplementedError("fast_deconstruct_by_modes (lstsq) is not on the CUDA path (SURVEY.md §8f rank 3)")
+        """beam2d.py:640-650: ``lstsq(MtM, Mt . vec(centre crop), rcond=None)[0]``.  ``Mt`` is the (M, K) stack of
+        flattened modes, ``MtM`` the (M, M) system matrix.  The projection ``Mt . f`` (M x K, the expensive
+        part) runs on the GPU (tensor cores for complex64); the M x M least-squares solve is the reference's own
+        ``numpy.linalg.lstsq`` call on the host (tiny, LAPACK)."""
+        proj = self.deconstruct_by_modes(modes_matrix_t, mode='scalar')
+        proj = self._np(proj) if not isinstance(proj, np.ndarray) else proj
+        mtm = np.asarray(self._np(modes_matrix_dot_t) if not isinstance(modes_matrix_dot_t, np.ndarray) else modes_matrix_dot_t)
+        if proj.ndim == 1:
+            sol = np.linalg.lstsq(mtm, proj, rcond=None)[0]
+        else:   # a batch of beams: one right-hand side per beam
+            sol = np.linalg.lstsq(mtm, proj.reshape(-1, proj.shape[-1]).T, rcond=None)[0].T.reshape(proj.shape)
+        self.modes_coeffs = sol.astype(self.complex) if sol.dtype != self.complex else sol
+        return self.modes_coeffs
 
     def construct_by_modes(self, modes_list, modes_coeffs):
         """beam2d.py:664-667: field = sum_i c_i * zero-padded mode_i; spectrum = fft2(field)."""

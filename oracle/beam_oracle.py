@@ -195,6 +195,17 @@ def modes_project(field: np.ndarray, modes: np.ndarray) -> np.ndarray:
     return np.vstack(modes) @ flat
 
 
+def modes_fast_lstsq(field: np.ndarray, modes_matrix_t: np.ndarray, modes_matrix_dot_t: np.ndarray) -> np.ndarray:
+    """fast_deconstruct_by_modes (beam2d.py:640-650): ``lstsq(MtM, Mt . vec(centre crop), rcond=None)[0]`` with
+    ``Mt`` of shape (M, K) (the stack of flattened modes) and ``MtM`` the (M, M) system matrix."""
+    modes_matrix_t = np.asarray(modes_matrix_t)
+    Nb = int(np.sqrt(modes_matrix_t.shape[1]))
+    n = field.shape[-1]
+    dN = (n - Nb) // 2
+    flat = field[dN:n - dN, dN:n - dN].flatten()
+    return np.linalg.lstsq(np.asarray(modes_matrix_dot_t), modes_matrix_t.dot(flat), rcond=None)[0]
+
+
 def modes_synthesize(modes: np.ndarray, coeffs: np.ndarray, npoints: int) -> np.ndarray:
     """beam2d.py:552-562 + :664-666: zero-pad every mode to the grid, sum_i c_i M_i."""
     modes = np.asarray(modes)
@@ -290,6 +301,9 @@ class OracleBeam:
 
     def deconstruct_by_modes(self, modes):
         return modes_project(self.field, modes)
+
+    def fast_deconstruct_by_modes(self, modes_matrix_t, modes_matrix_dot_t):
+        return modes_fast_lstsq(self.field, modes_matrix_t, modes_matrix_dot_t)
 
     def construct_by_modes(self, modes, coeffs):
         self.field = modes_synthesize(modes, coeffs, self.npoints)

@@ -131,6 +131,10 @@ def test_golden_modes(bits):
     b = Beam2D(200 * um, 64, 632 * nm, init_field_gen=lp.random_wave, complex_bits=bits)
     c = b.deconstruct_by_modes(g["modes"])
     assert rel_l2(c, g["coeffs"]) <= TOL[bits]
+    mt = np.vstack(g["modes"])
+    cf = b.fast_deconstruct_by_modes(mt, mt.dot(mt.T))          # beam2d.py:640-650
+    # the M x M system of 6 random modes is well conditioned (cond ~ 2): the projection error carries over
+    assert rel_l2(cf, g["coeffs_fast"]) <= 10 * TOL[bits]
     b.construct_by_modes(g["modes"], c)
     assert rel_l2(b.field, g["field"]) <= TOL[bits]
     assert rel_l2(b.spectrum, g["spectrum"]) <= TOL[bits]
