@@ -47,8 +47,8 @@ template <typename C> __device__ __forceinline__ C cconj(C a) { C r; r.x = a.x; 
 // a complex sample is one 64-bit register pair, a complex add is ONE instruction, a complex
 // multiply is two.  The half swap, the per-half negation and the scalar broadcast written
 // below with make_float2 are operand modifiers of those instructions (R.F32x2.LO_HI, .NP,
-// R.F32), not extra moves.  Enabled per translation unit with LP2D_PACKED_F32 (the pipeline
-// kernels, which are issue bound); the one-kernel-per-pass line kernels are latency bound and
+// R.F32), not extra moves.  Enabled per translation unit with LP2D_PACKED_F32 (the fused step
+// kernel, which is issue bound); the one-kernel-per-pass line kernels are latency bound and
 // measured ~5 % slower with the pair-aligned register allocation, so they keep scalar FP32.
 #if defined(LP2D_PACKED_F32) && defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
 template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b) { return __fadd2_rn(a, b); }

@@ -1,4 +1,4 @@
-"""Sweep the scheduling knobs of the persistent pipeline kernel (group size, lag, ring slots, grid)."""
+"""Sweep the knobs of the fused step kernel (beams per item, lag, ring slots, hints, variant, which steps use it)."""
 import ctypes as C
 import itertools
 import os
@@ -29,7 +29,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     bits = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     batch = int(sys.argv[3]) if len(sys.argv) > 3 else 256
-    combos = sys.argv[4] if len(sys.argv) > 4 else "G=1,2,4;LAG=0;SLOTS=0;GRID=0;RING=48"
+    combos = sys.argv[4] if len(sys.argv) > 4 else "PIPE=2;G=0,1,2;LAG=0;SLOTS=0"
     keys, vals = [], []
     for kv in combos.split(";"):
         k, v = kv.split("=")
@@ -44,8 +44,8 @@ def main():
     hbm = 6535.1e9
     print(f"n={n} bits={bits} batch={batch}; us/beam (fraction of {hbm/1e9:.0f} GB/s on algorithmic bytes)")
     print(" ".join(f"{k:>6s}" for k in keys) + " | fft2(2PB) | stateful(3PB) | fresh f->f(2PB)")
-    envname = {"G": "LP2D_PIPE_G", "LAG": "LP2D_PIPE_LAG", "SLOTS": "LP2D_PIPE_SLOTS", "GRID": "LP2D_PIPE_GRID",
-               "RING": "LP2D_RING_MB", "PIPE": "LP2D_PIPE", "VAR": "LP2D_PIPE_VARIANT", "MODE": "LP2D_PIPE_MODE", "HINTS": "LP2D_PIPE_HINTS", "PERSIST": "LP2D_PIPE_PERSIST", "OPS": "LP2D_FUSED_OPS"}
+    envname = {"G": "LP2D_PIPE_G", "LAG": "LP2D_PIPE_LAG", "SLOTS": "LP2D_PIPE_SLOTS", 
+               "RING": "LP2D_RING_MB", "PIPE": "LP2D_PIPE", "VAR": "LP2D_PIPE_VARIANT", "HINTS": "LP2D_PIPE_HINTS", "PERSIST": "LP2D_PIPE_PERSIST", "OPS": "LP2D_FUSED_OPS", "TMA": "LP2D_TMA"}
     for combo in itertools.product(*vals):
         for k, v in zip(keys, combo):
             os.environ[envname[k]] = v
