@@ -216,29 +216,50 @@ __global__ void modes_project_kernel(const cx<T>* __restrict__ field, const cx<T
 }
 
 // SIMT mode synthesis: field_b[r][c] = sum_k coeffs[b][k] * M[k][crop^-1(r, c)], zero outside the
-// centred nb x nb window (beam2d.py:552-562, 664-666).
-template <typename T>
-__global__ void modes_synthesize_kernel(const cx<T>* __restrict__ coeffs, const cx<T>* __restrict__ modes,
-                                        cx<T>* __restrict__ field, int n, int nb, int nmodes) {
-    const long long b = blockIdx.y;
+// centred nb x nb window (beam2d.py:552-562, 664-666).  The mode matrix is the big operand (nmodes x nb^2):
+// a thread owns one grid point and BT beams, so a mode sample is loaded once per BT beams; the coefficients
+// of the beam tile are staged in shared memory MC modes at a time and read as warp broadcasts.  Accumulation
+// in the field's real type (at most a few hundred terms per sum).
+template <typename T, int BT, int MC>
+__global__ void __launch_bounds__(256) modes_synthesize_kernel(const cx<T>* __restrict__ coeffs, const cx<T>* __restrict__ modes,
+                                                               cx<T>* __restrict__ field, int n, int nb, int nmodes, long long batch) {
+    __shared__ cx<T> sc[MC][BT];
+    const long long b0 = (long long)blockIdx.y * BT;
     const int dn = (n - nb) / 2;
     const int nt = n - dn;
     const long long total = (long long)n * n;
-    const cx<T>* cb = coeffs + b * nmodes;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % n), r = (int)(i / n);
-        double ax = 0, ay = 0;
-        if (r >= dn && r < nt && c >= dn && c < nt) {
-            const long long p = (long long)(r - dn) * nb + (c - dn);
-            for (int k = 0; k < nmodes; ++k) {
-                const cx<T> mv = modes[(long long)k * nb * nb + p];
-                const cx<T> cv = cb[k];
-                ax += (double)mv.x * cv.x - (double)mv.y * cv.y;
-                ay += (double)mv.x * cv.y + (double)mv.y * cv.x;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(i % n), r = (int)(i / n);
+    const bool inside = i < total && r >= dn && r < nt && c >= dn && c < nt;
+    const long long p = inside ? (long long)(r - dn) * nb + (c - dn) : 0;
+    const long long kk = (long long)nb * nb;
+    cx<T> acc[BT];
+#pragma unroll
+    for (int j = 0; j < BT; ++j) acc[j] = mk<T>((T)0, (T)0);
+    for (int k0 = 0; k0 < nmodes; k0 += MC) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < MC * BT; q += blockDim.x) {
+            const int k = q / BT, j = q % BT;
+            sc[k][j] = (k0 + k < nmodes && b0 + j < batch) ? coeffs[(b0 + j) * nmodes + k0 + k] : mk<T>((T)0, (T)0);
+        }
+        __syncthreads();
+        if (inside) {
+            const int kn = (nmodes - k0 < MC) ? nmodes - k0 : MC;
+            for (int k = 0; k < kn; ++k) {
+                const cx<T> mv = __ldg(&modes[(long long)(k0 + k) * kk + p]);
+#pragma unroll
+                for (int j = 0; j < BT; ++j) {
+                    const cx<T> cv = sc[k][j];
+                    acc[j].x += mv.x * cv.x - mv.y * cv.y;
+                    acc[j].y += mv.x * cv.y + mv.y * cv.x;
+                }
             }
         }
-        field[b * total + i] = mk<T>((T)ax, (T)ay);
+    }
+    if (i < total) {
+#pragma unroll
+        for (int j = 0; j < BT; ++j)
+            if (b0 + j < batch) __stcs(&field[(b0 + j) * total + i], acc[j]);
     }
 }
 
@@ -376,11 +397,16 @@ int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void
         return set_error(LP2D_EINVAL, "modes_synthesize: bad arguments");
     if (batch == 0) return LP2D_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    dim3 grid(grid_for((long long)n * n, 256), (unsigned)batch);
-    if (dtype == LP2D_C64)
-        modes_synthesize_kernel<float><<<grid, 256, 0, s>>>((const float2*)coeffs, (const float2*)modes, (float2*)field, n, nb, nmodes);
-    else
-        modes_synthesize_kernel<double><<<grid, 256, 0, s>>>((const double2*)coeffs, (const double2*)modes, (double2*)field, n, nb, nmodes);
+    const unsigned gx = (unsigned)(((long long)n * n + 255) / 256);
+    if (dtype == LP2D_C64) {
+        constexpr int BT = 8;
+        dim3 grid(gx, (unsigned)((batch + BT - 1) / BT));
+        modes_synthesize_kernel<float, BT, 128><<<grid, 256, 0, s>>>((const float2*)coeffs, (const float2*)modes, (float2*)field, n, nb, nmodes, batch);
+    } else {
+        constexpr int BT = 4;
+        dim3 grid(gx, (unsigned)((batch + BT - 1) / BT));
+        modes_synthesize_kernel<double, BT, 128><<<grid, 256, 0, s>>>((const double2*)coeffs, (const double2*)modes, (double2*)field, n, nb, nmodes, batch);
+    }
     return done("modes_synthesize launch");
 }
 

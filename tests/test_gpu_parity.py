@@ -583,3 +583,22 @@ def test_fused_step_tma_column_stage():
         o.propagate(z)
     assert rel_l2(res["1"][0], o.field) <= TOL[64]
     assert rel_l2(res["1"][2], o.iprofile) <= TOL[64]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits", BITS)
+def test_modes_synthesize_batched(bits):
+    """construct_by_modes (beam2d.py:552-562, 664-666) for a ragged batch: field_b = sum_i c[b][i] * zero-padded
+    mode_i, against the reference's einsum expression in complex128; spectrum = fft2(field)."""
+    n, nb, nmodes, batch = 128, 64, 150, 11
+    rng = np.random.default_rng(3)
+    modes = (rng.standard_normal((nmodes, nb * nb)) + 1j * rng.standard_normal((nmodes, nb * nb))).astype(CT[bits])
+    coeffs = (rng.standard_normal((batch, nmodes)) + 1j * rng.standard_normal((batch, nmodes))).astype(CT[bits])
+    b = Beam2D(200 * um, n, 632 * nm, init_field=np.zeros((batch, n, n), dtype=CT[bits]), complex_bits=bits)
+    b.construct_by_modes(modes, coeffs)
+    dn = (n - nb) // 2
+    exact = np.zeros((batch, n, n), dtype=np.complex128)
+    exact[:, dn:n - dn, dn:n - dn] = np.einsum('ijk,bi->bjk', modes.astype(np.complex128).reshape(nmodes, nb, nb),
+                                               coeffs.astype(np.complex128))
+    assert rel_l2(b.field, exact) <= TOL[bits]
+    assert rel_l2(b.spectrum, np.fft.fft2(exact)) <= TOL[bits]
