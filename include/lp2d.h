@@ -55,6 +55,11 @@ LP2D_API const char* lp2d_last_error(void);
 /* Smallest / largest supported npoints (powers of two in between are supported). */
 LP2D_API int lp2d_min_npoints(void);
 LP2D_API int lp2d_max_npoints(int dtype);
+/* Longest line lp2d_pass_lines transforms.  Plans of lp2d_max_npoints < n <= this hold line kernels
+ * only (one line spread over a thread-block cluster): every 2-D entry point returns
+ * LP2D_EUNSUPPORTED for them and the grid is driven as a slab decomposition (slab.py), also on
+ * one GPU. */
+LP2D_API int lp2d_max_line_points(int dtype);
 
 /* Host helper: the grids of Beam2D._construct_grids (beam2d.py:299-308) with the
  * same IEEE operation order: dL = area/n; X[k] = (k - ceil(n/2)) * dL for the

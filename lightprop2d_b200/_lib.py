@@ -23,6 +23,7 @@ SIGNATURES = {
     "lp2d_last_error": (C.c_char_p, []),
     "lp2d_min_npoints": (_i, []),
     "lp2d_max_npoints": (_i, [_i]),
+    "lp2d_max_line_points": (_i, [_i]),
     "lp2d_grid_tables": (_i, [_i, _d, _d, _dp, _dp, _dp, _dp, _dp]),
     "lp2d_plan_create": (_i, [C.POINTER(_vp), _i, _i, _dp, _dp, _dp]),
     "lp2d_plan_destroy": (_i, [_vp]),

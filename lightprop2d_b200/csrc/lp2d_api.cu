@@ -9,6 +9,7 @@
 #include "../../include/lp2d.h"
 #include "dispatch.h"
 #include "pipe2_ops.cuh"
+#include "xl_line.cuh"
 
 namespace lp2d {
 long long g_launches = 0;
@@ -75,6 +76,8 @@ struct lp2d_plan {
     int dtype;
     const SizeOps<float>* ops32;
     const SizeOps<double>* ops64;
+    const XlOps<float>* xl32;      // long lines (cluster kernel): lp2d_pass_lines only, no 2-D step
+    const XlOps<double>* xl64;
     void* tw;          // device twiddles (cx<T>)
     double* tabs;      // device: a | b | x2, n doubles each
     long long chunk_bytes;   // intermediate kept per kernel pair (L2 residency)
@@ -112,6 +115,13 @@ struct lp2d_plan {
     do {                                                                        \
         if ((p) == nullptr) return fail(LP2D_EINVAL, "plan is NULL");           \
     } while (0)
+// entry points that need the 2-D kernel set (plans of more than lp2d_max_npoints points hold line kernels only)
+#define LP2D_CHECK_2D(p)                                                                                   \
+    do {                                                                                                   \
+        if ((p) == nullptr) return fail(LP2D_EINVAL, "plan is NULL");                                      \
+        if ((p)->ops32 == nullptr && (p)->ops64 == nullptr)                                                \
+            return fail(LP2D_EUNSUPPORTED, "npoints above lp2d_max_npoints: only lp2d_pass_lines (the slab-decomposed grid) is available"); \
+    } while (0)
 
 extern "C" {
 
@@ -120,6 +130,7 @@ const char* lp2d_last_error(void) { return t_err.c_str(); }
 long long lp2d_launch_count(void) { return g_launches; }
 int lp2d_min_npoints(void) { return 16; }
 int lp2d_max_npoints(int dtype) { return dtype == LP2D_C64 ? 8192 : 4096; }
+int lp2d_max_line_points(int dtype) { (void)dtype; return 32768; }
 
 int lp2d_grid_tables(int n, double area_size, double wl, double* X, double* Kx, double* a,
                      double* b, double* x2) {
@@ -154,19 +165,22 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     const int variant = venv ? atoi(venv) : 0;
     const SizeOps<float>* o32 = dtype == LP2D_C64 ? find_ops_f32(n, variant) : nullptr;
     const SizeOps<double>* o64 = dtype == LP2D_C128 ? find_ops_f64(n, variant) : nullptr;
-    if (o32 == nullptr && o64 == nullptr) {
+    const XlOps<float>* x32 = (dtype == LP2D_C64 && o32 == nullptr) ? find_xl_f32(n) : nullptr;
+    const XlOps<double>* x64 = (dtype == LP2D_C128 && o64 == nullptr) ? find_xl_f64(n) : nullptr;
+    if (o32 == nullptr && o64 == nullptr && x32 == nullptr && x64 == nullptr) {
         char buf[160];
         snprintf(buf, sizeof buf, "plan_create: npoints=%d not supported for %s (powers of two %d..%d)", n,
-                 dtype == LP2D_C64 ? "complex64" : "complex128", lp2d_min_npoints(), lp2d_max_npoints(dtype));
+                 dtype == LP2D_C64 ? "complex64" : "complex128", lp2d_min_npoints(), lp2d_max_line_points(dtype));
         return fail(LP2D_EUNSUPPORTED, buf);
     }
     cudaError_t e;
     int dev = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    if ((e = (o32 ? o32->configure() : o64->configure())) != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    if ((e = (o32 ? o32->configure() : o64 ? o64->configure() : x32 ? x32->configure() : x64->configure())) != cudaSuccess)
+        return cuda_fail(e, "cudaFuncSetAttribute");
 
     lp2d_plan* p = new lp2d_plan();
-    p->device = dev; p->n = n; p->dtype = dtype; p->ops32 = o32; p->ops64 = o64;
+    p->device = dev; p->n = n; p->dtype = dtype; p->ops32 = o32; p->ops64 = o64; p->xl32 = x32; p->xl64 = x64;
     p->tw = nullptr; p->tabs = nullptr;
     const char* env = getenv("LP2D_CHUNK_MB");
     p->chunk_bytes = (env ? atoll(env) : 32) * (1ll << 20);
@@ -191,7 +205,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     }
 
     std::vector<double> w;
-    if (o32) o32->twiddles(w); else o64->twiddles(w);
+    if (o32) o32->twiddles(w); else if (o64) o64->twiddles(w); else if (x32) x32->twiddles(w); else x64->twiddles(w);
     const size_t ntw = w.size() / 2;
     const size_t tw_bytes = (ntw ? ntw : 1) * (dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2));
     if ((e = cudaMalloc(&p->tw, tw_bytes)) != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(twiddles)"); }
@@ -284,6 +298,12 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
 
 int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
     if (p == nullptr) return 0;
+    if (p->ops32 == nullptr && p->ops64 == nullptr) {
+        if (name != nullptr && name_len > 0)
+            snprintf(name, (size_t)name_len, "xl_line_kernel<%s, N=%d, E=%d, CL=%d> cluster line pass", p->dtype == LP2D_C64 ? "float" : "double",
+                     p->n, p->xl32 ? p->xl32->e : p->xl64->e, p->xl32 ? p->xl32->cl : p->xl64->cl);
+        return 0;
+    }
     const bool fused = (p->p2_32 != nullptr || p->p2_64 != nullptr) && (p->fused_ops & 2);
     if (name != nullptr && name_len > 0) {
         if (fused) {
@@ -329,6 +349,10 @@ namespace {
 template <typename T> const SizeOps<T>* ops_of(const lp2d_plan* p);
 template <> const SizeOps<float>* ops_of<float>(const lp2d_plan* p) { return p->ops32; }
 template <> const SizeOps<double>* ops_of<double>(const lp2d_plan* p) { return p->ops64; }
+
+template <typename T> const XlOps<T>* xl_of(const lp2d_plan* p);
+template <> const XlOps<float>* xl_of<float>(const lp2d_plan* p) { return p->xl32; }
+template <> const XlOps<double>* xl_of<double>(const lp2d_plan* p) { return p->xl64; }
 
 template <typename T> const P2Ops<T>* p2_of(const lp2d_plan* p);
 template <> const P2Ops<float>* p2_of<float>(const lp2d_plan* p) { return p->p2_32; }
@@ -684,7 +708,7 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
 extern "C" {
 
 int lp2d_fft2(lp2d_plan* p, const void* in, void* out, long long batch, int inverse, void* stream) {
-    LP2D_CHECK_PLAN(p);
+    LP2D_CHECK_2D(p);
     if (in == nullptr || out == nullptr || batch < 0) return fail(LP2D_EINVAL, "fft2: NULL pointer or negative batch");
     if (batch == 0) return LP2D_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -695,7 +719,7 @@ int lp2d_fft2(lp2d_plan* p, const void* in, void* out, long long batch, int inve
 
 int lp2d_propagate(lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
                    void* stream) {
-    LP2D_CHECK_PLAN(p);
+    LP2D_CHECK_2D(p);
     if (spectrum == nullptr || field == nullptr || batch < 0) return fail(LP2D_EINVAL, "propagate: NULL pointer or negative batch");
     if (spectrum == field) return fail(LP2D_EINVAL, "propagate: spectrum and field must be distinct buffers");
     if (batch == 0) return LP2D_OK;
@@ -706,7 +730,7 @@ int lp2d_propagate(lp2d_plan* p, void* spectrum, void* field, void* intensity, l
 
 int lp2d_propagate_field(lp2d_plan* p, const void* field_in, void* field_out, void* spectrum_out, void* intensity,
                          void* work, long long work_bytes, long long batch, double z, void* stream) {
-    LP2D_CHECK_PLAN(p);
+    LP2D_CHECK_2D(p);
     if (field_in == nullptr || batch < 0) return fail(LP2D_EINVAL, "propagate_field: NULL input or negative batch");
     if (field_out == nullptr && intensity == nullptr && spectrum_out == nullptr)
         return fail(LP2D_EINVAL, "propagate_field: no output requested");
@@ -718,7 +742,7 @@ int lp2d_propagate_field(lp2d_plan* p, const void* field_in, void* field_out, vo
 }
 
 int lp2d_lens(lp2d_plan* p, void* field, void* spectrum, long long batch, double k0, double f, void* stream) {
-    LP2D_CHECK_PLAN(p);
+    LP2D_CHECK_2D(p);
     if (field == nullptr || spectrum == nullptr || batch < 0) return fail(LP2D_EINVAL, "lens: NULL pointer or negative batch");
     if (field == spectrum) return fail(LP2D_EINVAL, "lens: field and spectrum must be distinct buffers");
     if (batch == 0) return LP2D_OK;
@@ -730,7 +754,7 @@ int lp2d_lens(lp2d_plan* p, void* field, void* spectrum, long long batch, double
 
 int lp2d_mul_fft2(lp2d_plan* p, void* data, void* other, const void* mask, int mask_kind, long long mask_beam_stride,
                   long long batch, int inverse, void* stream) {
-    LP2D_CHECK_PLAN(p);
+    LP2D_CHECK_2D(p);
     if (data == nullptr || other == nullptr || batch < 0) return fail(LP2D_EINVAL, "mul_fft2: NULL pointer or negative batch");
     if (data == other) return fail(LP2D_EINVAL, "mul_fft2: data and other must be distinct buffers");
     if (mask != nullptr && (mask_kind < LP2D_MASK_COMPLEX || mask_kind > LP2D_MASK_U8))
@@ -745,7 +769,7 @@ int lp2d_mul_fft2(lp2d_plan* p, void* data, void* other, const void* mask, int m
 
 int lp2d_pass(lp2d_plan* p, int axis, int op, const void* in, void* out, void* out_state, void* intensity,
               long long batch, int inverse, double z, void* stream) {
-    LP2D_CHECK_PLAN(p);
+    LP2D_CHECK_2D(p);
     if (in == nullptr || batch < 0 || (axis != LP2D_AXIS_ROWS && axis != LP2D_AXIS_COLS))
         return fail(LP2D_EINVAL, "pass: bad arguments");
     if (op < LP2D_OP_FFT || op > LP2D_OP_FFT_H_IFFT) return fail(LP2D_EINVAL, "pass: unknown op");
@@ -794,6 +818,10 @@ int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_s
         a.z = z;                                                                                  \
         a.groups = 1; a.group_beams = 1; a.nbeams = 1;                                            \
         a.line0 = line0; a.nlines = nlines;                                                       \
+        if (ops_of<T>(p) == nullptr) {                                                            \
+            LP2D_CU(xl_of<T>(p)->launch(op == LP2D_OP_H_FFT ? PRE_H : PRE_NONE, a, s), "cluster line pass launch"); \
+            return LP2D_OK;                                                                       \
+        }                                                                                         \
         LP2D_CU(ops_of<T>(p)->row(op == LP2D_OP_H_FFT ? PRE_H : PRE_NONE, a, s), "slab row pass launch"); \
         return LP2D_OK;                                                                           \
     }

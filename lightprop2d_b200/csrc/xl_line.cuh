@@ -1,0 +1,237 @@
+// Long lines: ONE 1-D transform spread over a thread-block cluster.
+//
+// A line of 16384 / 32768 complex64 samples (128 / 256 KB) no longer fits the registers and the
+// shared memory of one CTA next to its Stockham exchange buffer.  Here a line belongs to a
+// cluster of CL CTAs: TPL = N / E threads in total, THREADS = TPL / CL per CTA, thread t (global
+// within the cluster) owns the samples t + TPL * m exactly as in fft_core.cuh, so loads and stores
+// stay HBM <-> registers, coalesced.  The padded exchange buffer of LINE_SLOTS samples is cut in
+// CL contiguous pieces, one per CTA; a scatter / gather goes to whichever CTA holds the slot
+// through distributed shared memory (mapa + ld/st.shared::cluster), and the two barriers of a
+// pass are cluster barriers.  Same pass schedule, same twiddle tables, same arithmetic as the
+// single-CTA line kernel (line_pass), so results agree with it to rounding.
+//
+// Used by lp2d_pass_lines (the row pass of the slab-decomposed grid, BASELINE.json config 4:
+// 32768^2 complex64 over 8 GPUs) for the sizes the single-CTA kernels do not cover.
+#pragma once
+#include <vector>
+#include <cmath>
+#include "dispatch.h"
+
+namespace lp2d {
+
+template <typename T> struct ClMem;
+template <> struct ClMem<float> {
+    __device__ __forceinline__ static float2 ld(unsigned a) {
+        float2 v;
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ static void st(unsigned a, float2 v) {
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+    }
+};
+template <> struct ClMem<double> {
+    __device__ __forceinline__ static double2 ld(unsigned a) {
+        double2 v;
+        asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ static void st(unsigned a, double2 v) {
+        asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+    }
+};
+
+template <int CL>
+__device__ __forceinline__ void xl_sync() {
+    if (CL == 1) {
+        __syncthreads();
+    } else {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+}
+
+template <typename T, int N, int E, int CL>
+struct XlCfg {
+    using LP = LinePlan<N, E>;
+    static constexpr int TPL = LP::TPL;
+    static constexpr int THREADS = TPL / CL;
+    static constexpr int CH = LP::LINE_SLOTS / CL;               // exchange slots held by one CTA
+    static constexpr size_t SMEM = (size_t)CH * sizeof(cx<T>);
+    static_assert(TPL % CL == 0 && LP::LINE_SLOTS % CL == 0, "cluster split");
+    static_assert(THREADS <= 1024 && THREADS % 32 == 0, "block size");
+    static_assert(SMEM <= 227 * 1024, "exchange piece does not fit an SM");
+    static_assert(CL >= 1 && CL <= 8, "portable cluster size");
+};
+
+// shared::cluster address of exchange slot `slot`
+template <typename T, int CL, int CH>
+__device__ __forceinline__ unsigned xl_addr(const unsigned (&sb)[CL], int slot) {
+    unsigned b = sb[0];
+    int off = slot;
+#pragma unroll
+    for (int r = 1; r < CL; ++r)
+        if (slot >= r * CH) { b = sb[r]; off = slot - r * CH; }
+    return b + (unsigned)off * (unsigned)sizeof(cx<T>);
+}
+
+// One Stockham pass (see line_pass in fft_core.cuh) with the exchange in distributed shared memory.
+template <typename T, int N, int E, int CL, int P>
+__device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* __restrict__ tw, int t) {
+    using LP = LinePlan<N, E>;
+    using K = XlCfg<T, N, E, CL>;
+    constexpr int R = LP::radix(P);
+    constexpr int Ns = LP::ns(P);
+    constexpr int Q = E / R;
+    constexpr int TPL = LP::TPL;
+    constexpr bool last = (Ns * R == N);
+    constexpr int twoff = LP::tw_offset(P);
+
+    if (P > 0) {
+        xl_sync<CL>();                       // the scatter of the previous pass is visible cluster-wide
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = ClMem<T>::ld(xl_addr<T, CL, K::CH>(sb, LP::pad(t + TPL * m)));
+    }
+    if (!last) xl_sync<CL>();                // everyone has read (and, at P = 0, every CTA of the cluster runs)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int j = t + TPL * q;
+        cx<T> u[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
+        if (Ns > 1) {
+            const int k = j & (Ns - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+        }
+        dft_reg<T, R>(u);
+        if (last) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[q + r * Q] = u[r];
+        } else {
+            const int base = (j / Ns) * (Ns * R) + (j & (Ns - 1));
+#pragma unroll
+            for (int r = 0; r < R; ++r) ClMem<T>::st(xl_addr<T, CL, K::CH>(sb, LP::pad(base + r * Ns)), u[r]);
+        }
+    }
+}
+
+template <typename T, int N, int E, int CL, int P = 0>
+__device__ __forceinline__ void xl_fft(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* tw, int t) {
+    xl_pass<T, N, E, CL, P>(v, sb, tw, t);
+    if constexpr (P + 1 < LinePlan<N, E>::npass()) xl_fft<T, N, E, CL, P + 1>(v, sb, tw, t);
+}
+
+// Row pass over lines p.line0 .. p.line0 + p.nlines - 1 (one line per cluster):
+//   load -> [transfer function H, computed per sample in FP64] -> [store state] -> (i)FFT -> scale
+//        -> [store] [store |.|^2]
+template <typename T, int N, int E, int CL, int PRE>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XlCfg<T, N, E, CL>::THREADS, 1)
+xl_line_kernel(const LineArgs<T> p) {
+    using K = XlCfg<T, N, E, CL>;
+    constexpr int TPL = K::TPL;
+    extern __shared__ __align__(16) unsigned char xl_smem[];
+
+    unsigned rank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    unsigned sb[CL];
+    {
+        const unsigned local = (unsigned)__cvta_generic_to_shared(xl_smem);
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {
+            if (CL == 1) sb[r] = local;
+            else asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(sb[r]) : "r"(local), "r"(r));
+        }
+    }
+    const int t = (int)rank * K::THREADS + (int)threadIdx.x;
+    const long long line = (long long)(blockIdx.x / CL) + p.line0;
+    const long long beam = line / N;
+    const int fixed = (int)(line % N);
+    const long long base = beam * p.beam_stride + (long long)fixed * N;
+    const bool inv = (p.flags & F_INVERSE) != 0;
+
+    cx<T> v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = __ldcs(&p.in[base + t + TPL * m]);
+
+    if constexpr (PRE == PRE_H) {
+        const double b_j = __ldg(&p.b_tab[fixed]);
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], transfer_factor<T>(__ldg(&p.a_tab[t + TPL * m]), b_j, p.z));
+    }
+    if (p.out_pre != nullptr) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) __stcs(&p.out_pre[base + t + TPL * m], v[m]);
+    }
+    if (inv) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    }
+    xl_fft<T, N, E, CL>(v, sb, p.tw, t);
+    if (inv) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
+    }
+    const T sc = p.scale;
+    if (sc != (T)1) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) { v[m].x *= sc; v[m].y *= sc; }
+    }
+    if (p.out != nullptr) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) __stcs(&p.out[base + t + TPL * m], v[m]);
+    }
+    if (p.inten != nullptr) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) __stcs(&p.inten[base + t + TPL * m], v[m].x * v[m].x + v[m].y * v[m].y);
+    }
+    // no CTA may exit while a peer can still gather from its shared memory
+    if (CL > 1) xl_sync<CL>();
+}
+
+template <typename T>
+struct XlOps {
+    int n, e, cl, tw_size;
+    cudaError_t (*launch)(int pre, const LineArgs<T>& a, cudaStream_t s);   // a.nlines lines from a.line0
+    cudaError_t (*configure)();
+    void (*twiddles)(std::vector<double>& re_im);
+};
+
+template <typename T, int N, int E, int CL>
+struct Xl {
+    using LP = LinePlan<N, E>;
+    using K = XlCfg<T, N, E, CL>;
+    template <int PRE>
+    static cudaError_t go(const LineArgs<T>& a, cudaStream_t s) {
+        xl_line_kernel<T, N, E, CL, PRE><<<(unsigned)a.nlines * CL, K::THREADS, K::SMEM, s>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t launch(int pre, const LineArgs<T>& a, cudaStream_t s) {
+        return pre == PRE_H ? go<PRE_H>(a, s) : pre == PRE_NONE ? go<PRE_NONE>(a, s) : cudaErrorInvalidValue;
+    }
+    static cudaError_t configure() {
+        cudaError_t e = cudaFuncSetAttribute(xl_line_kernel<T, N, E, CL, PRE_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(xl_line_kernel<T, N, E, CL, PRE_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+    }
+    // same table layout as Ops::twiddles (sizes.cuh)
+    static void twiddles(std::vector<double>& w) {
+        w.assign(2 * (size_t)LP::tw_size(), 0.0);
+        const long double two_pi = 6.283185307179586476925286766559005768L;
+        for (int p = 1; p < LP::npass(); ++p) {
+            const int R = LP::radix(p), Ns = LP::ns(p), off = LP::tw_offset(p);
+            for (int r = 1; r < R; ++r)
+                for (int k = 0; k < Ns; ++k) {
+                    const long double ang = -two_pi * (long double)((long long)k * r) / (long double)((long long)Ns * R);
+                    w[2 * (size_t)(off + (r - 1) * Ns + k)] = (double)cosl(ang);
+                    w[2 * (size_t)(off + (r - 1) * Ns + k) + 1] = (double)sinl(ang);
+                }
+        }
+    }
+    static constexpr XlOps<T> entry() { return XlOps<T>{N, E, CL, LP::tw_size(), &launch, &configure, &twiddles}; }
+};
+
+const XlOps<float>* find_xl_f32(int n);
+const XlOps<double>* find_xl_f64(int n);
+
+}  // namespace lp2d

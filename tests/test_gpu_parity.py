@@ -401,6 +401,67 @@ def test_pass_lines_partial_slab_equals_full_pass():
     assert torch.equal(ref, out)
 
 
+# ----------------------------------------------------------------------------- long lines (cluster kernel)
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,n", [(64, 16384), (64, 32768), (128, 8192), (128, 16384), (128, 32768)])
+def test_long_line_kernel_matches_numpy(bits, n, tol):
+    """xl_line_kernel (one line over a thread-block cluster, exchange through distributed shared memory):
+    forward / inverse line transforms, the fused H multiply with the state store and |.|^2, at an
+    interior line offset, against numpy on the same lines (beam2d.py:485-490 restricted to rows)."""
+    from lightprop2d_b200.slab import CudaLineBackend
+    from oracle import beam_oracle as orc
+    area, wl, z = 200 * lp.um * n / 256, 632 * lp.nm, 100 * lp.um
+    be = CudaLineBackend(area, n, wl, bits)
+    rng = np.random.default_rng(n + bits)
+    ct = np.complex64 if bits == 64 else np.complex128
+    rows, line0 = 5, n // 2 - 2                       # lines on both sides of the fftfreq sign change
+    x = (rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))).astype(ct)
+    xd = torch.from_numpy(x).cuda()
+    assert rel_l2(be.lines(xd, line0).cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=1)) <= tol[bits]
+    assert rel_l2(be.lines(xd, line0, inverse=True).cpu().numpy(), np.fft.ifft(x.astype(np.complex128), axis=1)) <= tol[bits]
+    a, b = orc.kz2_tables(area, n, wl)
+    with np.errstate(invalid="ignore"):
+        kz = np.nan_to_num(np.sqrt(a[None, :] - b[line0:line0 + rows, None]))
+    ph = orc.transfer_phase(kz, z)
+    xs = x.copy()
+    xs *= np.cos(ph) + 1j * np.sin(ph)                # in-place multiply in the field dtype, as beam2d.py:489
+    state, inten = torch.empty_like(xd), be.empty(rows, n, real=True)
+    out = be.lines(xd, line0, inverse=True, z=z, state_out=state, intensity=inten)
+    want = np.fft.ifft(xs.astype(np.complex128), axis=1)
+    assert rel_l2(state.cpu().numpy(), xs) <= tol[bits]
+    assert rel_l2(out.cpu().numpy(), want) <= tol[bits]
+    assert rel_l2(inten.cpu().numpy(), np.abs(want) ** 2) <= tol[bits]
+    # transposed orientation (second plan: tables swapped and negated), in place
+    with np.errstate(invalid="ignore"):
+        kzt = np.nan_to_num(np.sqrt(a[line0:line0 + rows, None] - b[None, :]))
+    pht = orc.transfer_phase(kzt, z)
+    xt = x.copy()
+    xt *= np.cos(pht) + 1j * np.sin(pht)
+    buf = xd.clone()
+    be.lines(buf, line0, inverse=True, transposed=True, z=z, out=buf)
+    assert rel_l2(buf.cpu().numpy(), np.fft.ifft(xt.astype(np.complex128), axis=1)) <= tol[bits]
+    lib = _lib.load()
+    assert lib.lp2d_max_line_points(_lib.C64 if bits == 64 else _lib.C128) >= n
+    if n > lib.lp2d_max_npoints(_lib.C64 if bits == 64 else _lib.C128):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        assert lib.lp2d_fft2(be.plan.handle, xd.data_ptr(), xd.data_ptr(), 1, 0, st) == 2   # 2-D entry points: unsupported
+
+
+@pytest.mark.gpu
+def test_slab_16384_plane_waves():
+    """One 16384^2 complex64 grid through the slab path on one GPU (cluster line kernel + transposing
+    pack): spectrum support, propagated field and propagate(z); propagate(-z) round trip against the
+    closed form for a sum of plane waves (tools/planewave_check.py), 1e-5 relative L2."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from tools import planewave_check as pw
+    n = 16384
+    res = pw.check(n, 64, 0.4 * n / 1024, 532e-7, 0.02)
+    torch.cuda.empty_cache()
+    assert res["spectrum"] <= 1e-5 and res["field"] <= 1e-5 and res["round_trip"] <= 1e-5, res
+
+
 # ----------------------------------------------------------------------------- tensor-core mode projection
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,nb,nmodes,batch", [(128, 64, 130, 1), (256, 128, 96, 70), (256, 256, 200, 5)])

@@ -2,7 +2,8 @@
 
     torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tools/slab_multi_gpu.py [n_check] [n_time]
 
-1. parity: an n_check^2 grid against the numpy oracle (complex64 1e-5, complex128 1e-12);
+1. parity: an n_check^2 grid against the numpy oracle (complex64 1e-5, complex128 1e-12), and the
+   n_time^2 grid against the closed form for a sum of plane waves (tools/planewave_check.py);
 2. timing: repeated propagate steps on an n_time^2 complex64 grid (spectrum resident, one exchange
    per step), CUDA events, max over ranks; prints one JSON line on rank 0.
 """
@@ -50,6 +51,13 @@ def main():
             res[f"c{bits}_field_rel_l2"], res[f"c{bits}_spectrum_rel_l2"] = ef, es
             assert ef <= tol and es <= tol, (bits, ef, es)
         del b
+    # full-size parity through the plane-wave closed form (the numpy oracle cannot hold the big grid)
+    from tools import planewave_check as pw
+    res["planewave_n"] = n_time
+    res["planewave_c64_rel_l2"] = pw.check(n_time, 64, 0.4 * n_time / 1024, 532e-7, 0.02, rank, world)
+    torch.cuda.empty_cache()
+    if rank == 0:
+        assert max(res["planewave_c64_rel_l2"].values()) <= 1e-5, res
     # timing
     n = n_time
     r0, r1 = slab_rows(n, rank, world)
