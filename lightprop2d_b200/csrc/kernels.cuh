@@ -28,12 +28,24 @@ enum { MID_NONE = 0, MID_H = 1 };
 enum { F_INVERSE = 1,
        F_IN_STREAM = 2,     // input is read once: evict-first loads
        F_OUT_STREAM = 4,    // output is not re-read soon: evict-first stores
-       F_STATE_STREAM = 8   // same for out_pre / out_mid
+       F_STATE_STREAM = 8,  // same for out_pre / out_mid
+       F_IN_L2WIDE = 16     // column tiles narrower than a 128-byte line: ask L2 to fetch the whole line on a miss
+                            // (the CTAs of the neighbouring tiles want its other sectors at about the same time)
 };
 
 // cache-policy aware accessors: streaming data must not push the inter-pass
 // intermediate out of L2
 template <typename C> __device__ __forceinline__ C ld_cx(const C* p, bool stream) { return stream ? __ldcs(p) : *p; }
+__device__ __forceinline__ float2 ld_wide(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.L2::128B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_wide(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.L2::128B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 template <typename C> __device__ __forceinline__ void st_cx(C* p, C v, bool stream) { if (stream) __stcs(p, v); else *p = v; }
 enum { MASK_NONE = 0, MASK_CX = 1, MASK_REAL = 2, MASK_U8 = 3 };
 
@@ -174,6 +186,7 @@ line_kernel(const LineArgs<T> p) {
     }
     constexpr long long STRIDE = (AXIS == AX_ROW) ? 1 : N;
     const bool in_stream = (p.flags & F_IN_STREAM) != 0;
+    const bool in_wide = AXIS == AX_COL && (p.flags & F_IN_L2WIDE) != 0;
     const bool out_stream = (p.flags & F_OUT_STREAM) != 0;
     const bool state_stream = (p.flags & F_STATE_STREAM) != 0;
     const bool inv = (p.flags & F_INVERSE) != 0;
@@ -200,7 +213,8 @@ line_kernel(const LineArgs<T> p) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int pos = t + TPL * m;
-            v[m] = active ? ld_cx(&p.in[gb + pos * STRIDE], in_stream) : mk<T>(0, 0);
+            if (AXIS == AX_COL && in_wide) v[m] = active ? ld_wide(&p.in[gb + pos * STRIDE]) : mk<T>(0, 0);
+            else v[m] = active ? ld_cx(&p.in[gb + pos * STRIDE], in_stream) : mk<T>(0, 0);
         }
 
         if (p.mask_kind != MASK_NONE && active) {

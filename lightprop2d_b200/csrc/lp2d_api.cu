@@ -165,8 +165,10 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     const int variant = venv ? atoi(venv) : 0;
     const SizeOps<float>* o32 = dtype == LP2D_C64 ? find_ops_f32(n, variant) : nullptr;
     const SizeOps<double>* o64 = dtype == LP2D_C128 ? find_ops_f64(n, variant) : nullptr;
-    const XlOps<float>* x32 = (dtype == LP2D_C64 && o32 == nullptr) ? find_xl_f32(n) : nullptr;
-    const XlOps<double>* x64 = (dtype == LP2D_C128 && o64 == nullptr) ? find_xl_f64(n) : nullptr;
+    const char* xenv = getenv("LP2D_XL_VARIANT");
+    const int xvar = xenv ? atoi(xenv) : 0;
+    const XlOps<float>* x32 = (dtype == LP2D_C64 && o32 == nullptr) ? find_xl_f32(n, xvar) : nullptr;
+    const XlOps<double>* x64 = (dtype == LP2D_C128 && o64 == nullptr) ? find_xl_f64(n, xvar) : nullptr;
     if (o32 == nullptr && o64 == nullptr && x32 == nullptr && x64 == nullptr) {
         char buf[160];
         snprintf(buf, sizeof buf, "plan_create: npoints=%d not supported for %s (powers of two %d..%d)", n,
@@ -543,6 +545,7 @@ int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream
     a.group_beams = beams;
     a.nbeams = beams;
     a.nlines = (int)(beams * (p->n / ops_of<T>(p)->w_col));
+    if ((p->hints & 4) && ops_of<T>(p)->w_col * (int)sizeof(cx<T>) < 128) a.flags |= F_IN_L2WIDE;
     LP2D_CU(ops_of<T>(p)->col(mid, a, s), "column pass launch");
     return LP2D_OK;
 }

@@ -57,6 +57,11 @@ struct XlCfg {
     static constexpr int THREADS = TPL / CL;
     static constexpr int CH = LP::LINE_SLOTS / CL;               // exchange slots held by one CTA
     static constexpr size_t SMEM = (size_t)CH * sizeof(cx<T>);
+    // resident CTAs per SM: registers (2 E sizeof(T)/4 for the data, as many again for the butterflies), shared memory, threads
+    static constexpr int REGS = (E * (int)sizeof(T) >= 128) ? 128 : 64;
+    static constexpr int MINB_R = 65536 / (THREADS * REGS), MINB_S = (int)((227 * 1024) / (SMEM + 1024)), MINB_T = 2048 / THREADS;
+    static constexpr int MINB0 = MINB_R < MINB_S ? (MINB_R < MINB_T ? MINB_R : MINB_T) : (MINB_S < MINB_T ? MINB_S : MINB_T);
+    static constexpr int MINB = MINB0 < 1 ? 1 : MINB0;
     static_assert(TPL % CL == 0 && LP::LINE_SLOTS % CL == 0, "cluster split");
     static_assert(THREADS <= 1024 && THREADS % 32 == 0, "block size");
     static_assert(SMEM <= 227 * 1024, "exchange piece does not fit an SM");
@@ -100,8 +105,21 @@ __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL],
         for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
         if (Ns > 1) {
             const int k = j & (Ns - 1);
+            if constexpr (R > 16) {
+                // radix 32: load and apply the twiddles eight at a time (register pressure, see line_pass)
 #pragma unroll
-            for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+                for (int r0 = 1; r0 < R; r0 += 8) {
+                    cx<T> w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (r0 + i < R) w[i] = __ldg(&tw[twoff + (r0 + i - 1) * Ns + k]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) if (r0 + i < R) u[r0 + i] = cmul(u[r0 + i], w[i]);
+                    asm volatile("" ::: "memory");
+                }
+            } else {
+#pragma unroll
+                for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+            }
         }
         dft_reg<T, R>(u);
         if (last) {
@@ -125,7 +143,7 @@ __device__ __forceinline__ void xl_fft(cx<T> (&v)[E], const unsigned (&sb)[CL], 
 //   load -> [transfer function H, computed per sample in FP64] -> [store state] -> (i)FFT -> scale
 //        -> [store] [store |.|^2]
 template <typename T, int N, int E, int CL, int PRE>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XlCfg<T, N, E, CL>::THREADS, 1)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XlCfg<T, N, E, CL>::THREADS, XlCfg<T, N, E, CL>::MINB)
 xl_line_kernel(const LineArgs<T> p) {
     using K = XlCfg<T, N, E, CL>;
     constexpr int TPL = K::TPL;
@@ -190,7 +208,7 @@ xl_line_kernel(const LineArgs<T> p) {
 
 template <typename T>
 struct XlOps {
-    int n, e, cl, tw_size;
+    int n, e, cl, tw_size, variant;
     cudaError_t (*launch)(int pre, const LineArgs<T>& a, cudaStream_t s);   // a.nlines lines from a.line0
     cudaError_t (*configure)();
     void (*twiddles)(std::vector<double>& re_im);
@@ -228,10 +246,10 @@ struct Xl {
                 }
         }
     }
-    static constexpr XlOps<T> entry() { return XlOps<T>{N, E, CL, LP::tw_size(), &launch, &configure, &twiddles}; }
+    static constexpr XlOps<T> entry(int variant = 0) { return XlOps<T>{N, E, CL, LP::tw_size(), variant, &launch, &configure, &twiddles}; }
 };
 
-const XlOps<float>* find_xl_f32(int n);
-const XlOps<double>* find_xl_f64(int n);
+const XlOps<float>* find_xl_f32(int n, int variant);
+const XlOps<double>* find_xl_f64(int n, int variant);
 
 }  // namespace lp2d
