@@ -135,6 +135,16 @@ LP2D_API int lp2d_pass(lp2d_plan* plan, int axis, int op, const void* in, void* 
 LP2D_API int lp2d_pass_lines(lp2d_plan* plan, int op, const void* in, void* out, void* out_state,
                     void* intensity, int line0, int nlines, int inverse, double z, void* stream);
 
+/* The same pass reading its lines straight from the receive buffer of the tile exchange, so that no
+ * unpack copy is needed: `in_tiles` holds n / tile tiles, tile c = (nlines x tile) samples row-major,
+ * and sample pos of slab line i is in_tiles[(pos / tile) * nlines * tile + i * tile + pos % tile] (what
+ * all_to_all of lp2d_pack_transpose output delivers, tile = n / ranks).  tile: a power of two dividing
+ * n.  out / out_state / intensity are contiguous slab lines as in lp2d_pass_lines and must not alias
+ * in_tiles. */
+LP2D_API int lp2d_pass_lines_tiles(lp2d_plan* plan, int op, const void* in_tiles, int tile, void* out,
+                          void* out_state, void* intensity, int line0, int nlines, int inverse,
+                          double z, void* stream);
+
 /* Transposing tile pack for the slab exchange: in is a (rows x ld) row-major slab; for every tile
  * c (0 .. ntiles-1) of `tile` columns, out[c] (tile x rows, contiguous) = transpose(in[:, c*tile :
  * (c+1)*tile]).  ntiles * tile == ld. */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "lp2d_mul_fft2": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _vp]),
     "lp2d_pass": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _i, _d, _vp]),
     "lp2d_pass_lines": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _vp]),
+    "lp2d_pass_lines_tiles": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _vp]),
     "lp2d_pack_transpose": (_i, [_i, _vp, _vp, _i, _i, _i, _vp]),
     "lp2d_intensity": (_i, [_vp, _vp, _vp, _ll, _vp]),
     "lp2d_expand": (_i, [_i, _vp, _vp, _i, _i, _ll, _vp]),

@@ -28,24 +28,12 @@ enum { MID_NONE = 0, MID_H = 1 };
 enum { F_INVERSE = 1,
        F_IN_STREAM = 2,     // input is read once: evict-first loads
        F_OUT_STREAM = 4,    // output is not re-read soon: evict-first stores
-       F_STATE_STREAM = 8,  // same for out_pre / out_mid
-       F_IN_L2WIDE = 16     // column tiles narrower than a 128-byte line: ask L2 to fetch the whole line on a miss
-                            // (the CTAs of the neighbouring tiles want its other sectors at about the same time)
+       F_STATE_STREAM = 8   // same for out_pre / out_mid
 };
 
 // cache-policy aware accessors: streaming data must not push the inter-pass
 // intermediate out of L2
 template <typename C> __device__ __forceinline__ C ld_cx(const C* p, bool stream) { return stream ? __ldcs(p) : *p; }
-__device__ __forceinline__ float2 ld_wide(const float2* p) {
-    float2 v;
-    asm volatile("ld.global.L2::128B.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double2 ld_wide(const double2* p) {
-    double2 v;
-    asm volatile("ld.global.L2::128B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
 template <typename C> __device__ __forceinline__ void st_cx(C* p, C v, bool stream) { if (stream) __stcs(p, v); else *p = v; }
 enum { MASK_NONE = 0, MASK_CX = 1, MASK_REAL = 2, MASK_U8 = 3 };
 
@@ -68,6 +56,8 @@ struct LineArgs {
     long long beam_stride;  // samples between consecutive beams (N*N)
     long long mask_beam_stride;  // 0: one mask for every beam
     int line0;              // rows only: global index of the first line of the launch (slab passes), else 0
+    int seg_shift;          // slab row passes only: != 0 -> `in` is the receive buffer of the tile exchange, n >> seg_shift
+    int seg_rows;           //   tiles of (seg_rows lines x (1 << seg_shift) samples), first line of the launch first
     int nlines;             // lines (rows) or column tiles in ONE group
     int groups;             // beam groups a CTA walks over (>= 1)
     long long group_beams;  // beams per group
@@ -167,8 +157,10 @@ line_kernel(const LineArgs<T> p) {
     // which line of which beam; "fixed" is the grid index that is constant along the line
     long long base, mbase, beam;
     int fixed;
+    int lrel = 0;                                             // line relative to the first line of the launch
     bool in_range;
     if constexpr (AXIS == AX_ROW) {
+        lrel = (int)blockIdx.x * W + l;
         const long long line = (long long)blockIdx.x * W + l + p.line0;
         in_range = line < (long long)p.line0 + p.nlines;
         beam = line / N;
@@ -186,7 +178,6 @@ line_kernel(const LineArgs<T> p) {
     }
     constexpr long long STRIDE = (AXIS == AX_ROW) ? 1 : N;
     const bool in_stream = (p.flags & F_IN_STREAM) != 0;
-    const bool in_wide = AXIS == AX_COL && (p.flags & F_IN_L2WIDE) != 0;
     const bool out_stream = (p.flags & F_OUT_STREAM) != 0;
     const bool state_stream = (p.flags & F_STATE_STREAM) != 0;
     const bool inv = (p.flags & F_INVERSE) != 0;
@@ -213,8 +204,13 @@ line_kernel(const LineArgs<T> p) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int pos = t + TPL * m;
-            if (AXIS == AX_COL && in_wide) v[m] = active ? ld_wide(&p.in[gb + pos * STRIDE]) : mk<T>(0, 0);
-            else v[m] = active ? ld_cx(&p.in[gb + pos * STRIDE], in_stream) : mk<T>(0, 0);
+            if (AXIS == AX_ROW && p.seg_shift) {
+                // input in all-to-all tiles: tile (pos >> seg_shift) holds seg_rows lines of (1 << seg_shift) samples
+                const long long si = ((((long long)(pos >> p.seg_shift) * p.seg_rows + lrel) << p.seg_shift) + (pos & ((1 << p.seg_shift) - 1)));
+                v[m] = active ? ld_cx(&p.in[si], in_stream) : mk<T>(0, 0);
+            } else {
+                v[m] = active ? ld_cx(&p.in[gb + pos * STRIDE], in_stream) : mk<T>(0, 0);
+            }
         }
 
         if (p.mask_kind != MASK_NONE && active) {

@@ -545,7 +545,6 @@ int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream
     a.group_beams = beams;
     a.nbeams = beams;
     a.nlines = (int)(beams * (p->n / ops_of<T>(p)->w_col));
-    if ((p->hints & 4) && ops_of<T>(p)->w_col * (int)sizeof(cx<T>) < 128) a.flags |= F_IN_L2WIDE;
     LP2D_CU(ops_of<T>(p)->col(mid, a, s), "column pass launch");
     return LP2D_OK;
 }
@@ -800,11 +799,20 @@ int lp2d_pass(lp2d_plan* p, int axis, int op, const void* in, void* out, void* o
 #undef LP2D_PASS_BODY
 }
 
-int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_state, void* intensity, int line0,
-                    int nlines, int inverse, double z, void* stream) {
+static int pass_lines_impl(lp2d_plan* p, int op, const void* in, int tile, void* out, void* out_state, void* intensity, int line0,
+                           int nlines, int inverse, double z, void* stream) {
     LP2D_CHECK_PLAN(p);
     if (in == nullptr || nlines < 0 || line0 < 0 || line0 + nlines > p->n) return fail(LP2D_EINVAL, "pass_lines: bad arguments");
     if (op != LP2D_OP_FFT && op != LP2D_OP_H_FFT) return fail(LP2D_EINVAL, "pass_lines: op must be LP2D_OP_FFT or LP2D_OP_H_FFT");
+    int seg_shift = 0;
+    if (tile != 0) {
+        if (tile < 1 || (tile & (tile - 1)) != 0 || p->n % tile != 0)
+            return fail(LP2D_EINVAL, "pass_lines_tiles: tile must be a power of two that divides npoints");
+        if (tile != p->n) {                            // one tile of n samples = the contiguous slab
+            while ((1 << seg_shift) < tile) ++seg_shift;
+            if (in == out || in == out_state) return fail(LP2D_EINVAL, "pass_lines_tiles: the tiled input cannot be transformed in place");
+        }
+    }
     if (nlines == 0) return LP2D_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const double sc = inverse ? 1.0 / (double)p->n : 1.0;
@@ -812,7 +820,7 @@ int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_s
 #define LP2D_LINES_BODY(T)                                                                        \
     {                                                                                             \
         LineArgs<T> a = base_args<T>(p);                                                          \
-        a.in = static_cast<const cx<T>*>(in) - back;                                              \
+        a.in = seg_shift ? static_cast<const cx<T>*>(in) : static_cast<const cx<T>*>(in) - back;  \
         a.out = out ? static_cast<cx<T>*>(out) - back : nullptr;                                  \
         a.out_pre = out_state ? static_cast<cx<T>*>(out_state) - back : nullptr;                  \
         a.inten = intensity ? static_cast<T*>(intensity) - back : nullptr;                        \
@@ -821,6 +829,7 @@ int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_s
         a.z = z;                                                                                  \
         a.groups = 1; a.group_beams = 1; a.nbeams = 1;                                            \
         a.line0 = line0; a.nlines = nlines;                                                       \
+        a.seg_shift = seg_shift; a.seg_rows = nlines;                                             \
         if (ops_of<T>(p) == nullptr) {                                                            \
             LP2D_CU(xl_of<T>(p)->launch(op == LP2D_OP_H_FFT ? PRE_H : PRE_NONE, a, s), "cluster line pass launch"); \
             return LP2D_OK;                                                                       \
@@ -830,6 +839,17 @@ int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_s
     }
     if (p->dtype == LP2D_C64) LP2D_LINES_BODY(float) else LP2D_LINES_BODY(double)
 #undef LP2D_LINES_BODY
+}
+
+int lp2d_pass_lines(lp2d_plan* p, int op, const void* in, void* out, void* out_state, void* intensity, int line0,
+                    int nlines, int inverse, double z, void* stream) {
+    return pass_lines_impl(p, op, in, 0, out, out_state, intensity, line0, nlines, inverse, z, stream);
+}
+
+int lp2d_pass_lines_tiles(lp2d_plan* p, int op, const void* in_tiles, int tile, void* out, void* out_state, void* intensity,
+                          int line0, int nlines, int inverse, double z, void* stream) {
+    if (tile <= 0) return fail(LP2D_EINVAL, "pass_lines_tiles: tile must be positive");
+    return pass_lines_impl(p, op, in_tiles, tile, out, out_state, intensity, line0, nlines, inverse, z, stream);
 }
 
 int lp2d_intensity(lp2d_plan* p, const void* field, void* out, long long batch, void* stream) {

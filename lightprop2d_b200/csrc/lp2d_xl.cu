@@ -8,9 +8,11 @@ static const XlOps<float> kXlF32[] = {
     Xl<float, 16384, 16, 2>::entry(1),
     Xl<float, 16384, 32, 1>::entry(2),
     Xl<float, 16384, 32, 2>::entry(3),
-    Xl<float, 32768, 16, 2>::entry(),
+    // measured (profiles/r1d_xl_variants.log): E = 32 (two exchanges instead of three) wins at 32768; more CTAs
+    // per line lose (a larger share of the exchange crosses SMs)
+    Xl<float, 32768, 32, 2>::entry(),
     Xl<float, 32768, 16, 4>::entry(1),
-    Xl<float, 32768, 32, 2>::entry(2),
+    Xl<float, 32768, 16, 2>::entry(2),
     Xl<float, 32768, 32, 4>::entry(3),
 };
 static const XlOps<double> kXlF64[] = {
@@ -18,9 +20,9 @@ static const XlOps<double> kXlF64[] = {
     Xl<double, 8192, 8, 2>::entry(1),
     Xl<double, 8192, 16, 1>::entry(2),
     Xl<double, 8192, 16, 2>::entry(3),
-    Xl<double, 16384, 8, 2>::entry(),
+    Xl<double, 16384, 16, 2>::entry(),
     Xl<double, 16384, 8, 4>::entry(1),
-    Xl<double, 16384, 16, 2>::entry(2),
+    Xl<double, 16384, 8, 2>::entry(2),
     Xl<double, 16384, 16, 4>::entry(3),
     Xl<double, 32768, 8, 4>::entry(),
     Xl<double, 32768, 16, 4>::entry(2),

@@ -168,8 +168,18 @@ xl_line_kernel(const LineArgs<T> p) {
     const bool inv = (p.flags & F_INVERSE) != 0;
 
     cx<T> v[E];
+    if (p.seg_shift) {
+        // input in all-to-all tiles (see LineArgs::seg_shift)
+        const int lrel = (int)(blockIdx.x / CL);
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = __ldcs(&p.in[base + t + TPL * m]);
+        for (int m = 0; m < E; ++m) {
+            const int pos = t + TPL * m;
+            v[m] = __ldcs(&p.in[(((long long)(pos >> p.seg_shift) * p.seg_rows + lrel) << p.seg_shift) + (pos & ((1 << p.seg_shift) - 1))]);
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = __ldcs(&p.in[base + t + TPL * m]);
+    }
 
     if constexpr (PRE == PRE_H) {
         const double b_j = __ldg(&p.b_tab[fixed]);

@@ -55,6 +55,7 @@ def kz2_tables(area_size: float, npoints: int, wl: float):
 
 class CudaLineBackend:
     """Row passes and the transposing pack of liblp2d.so on the current CUDA device."""
+    reads_tiles = True      # lines() accepts the (G, rows, tile) receive buffer of the exchange
 
     def __init__(self, area_size, npoints, wl, complex_bits, device=None):
         import torch
@@ -81,15 +82,21 @@ class CudaLineBackend:
 
     def lines(self, x, line0, inverse=False, transposed=False, z=None, state_out=None, intensity=None, out=None):
         """(i)FFT along the last axis of the slab ``x`` (lines line0 .. line0 + rows - 1 of the plane).
-        With ``z``: x *= H(z) first (H in the slab's orientation), the product goes to ``state_out``."""
+        With ``z``: x *= H(z) first (H in the slab's orientation), the product goes to ``state_out``.
+        ``x`` is either the ``(rows, n)`` slab or the ``(n // tile, rows, tile)`` receive buffer of the tile
+        exchange (``exchange_transpose(..., tiles=True)``), which the kernel reads in place of an unpacked copy."""
         plan = self.plan_t if transposed else self.plan
-        out = self.empty(*x.shape) if out is None else out
+        tiled = x.dim() == 3
+        rows = int(x.shape[1] if tiled else x.shape[0])
+        out = self.empty(rows, self.n) if out is None else out
         op = _lib.OP_FFT if z is None else _lib.OP_H_FFT
-        _lib.check(self.lib.lp2d_pass_lines(plan.handle, op, x.data_ptr(), out.data_ptr(),
-                                            None if state_out is None else state_out.data_ptr(),
-                                            None if intensity is None else intensity.data_ptr(),
-                                            int(line0), int(x.shape[0]), 1 if inverse else 0,
-                                            0.0 if z is None else float(z), self._stream()), "pass_lines")
+        tail = (None if state_out is None else state_out.data_ptr(), None if intensity is None else intensity.data_ptr(),
+                int(line0), rows, 1 if inverse else 0, 0.0 if z is None else float(z), self._stream())
+        if tiled:
+            _lib.check(self.lib.lp2d_pass_lines_tiles(plan.handle, op, x.data_ptr(), int(x.shape[2]), out.data_ptr(), *tail),
+                       "pass_lines_tiles")
+        else:
+            _lib.check(self.lib.lp2d_pass_lines(plan.handle, op, x.data_ptr(), out.data_ptr(), *tail), "pass_lines")
         return out
 
     def pack_transpose(self, x, tile):
@@ -101,11 +108,13 @@ class CudaLineBackend:
         return out
 
 
-def exchange_transpose(x, backend, group=None):
+def exchange_transpose(x, backend, group=None, tiles=False):
     """All-to-all transpose of a slab-decomposed N x N array.
 
     ``x`` is this rank's ``(N/G, N)`` slab of A (rows ``r*N/G ..``).  Returns this rank's
-    ``(N/G, N)`` slab of A^T.  The same call maps the transposed layout back.
+    ``(N/G, N)`` slab of A^T.  The same call maps the transposed layout back.  With ``tiles=True`` (and a
+    backend whose line pass reads tiles, ``backend.reads_tiles``) the receive buffer ``(G, N/G, N/G)`` is
+    returned as it is -- ``out[r][i][k] = A^T[i][r*N/G + k]`` -- and the unpack copy is skipped.
     """
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -119,7 +128,11 @@ def exchange_transpose(x, backend, group=None):
         recv = send.new_empty(send.shape)
         dist.all_to_all_single(recv, send, group=group)   # recv[r] = tile (this rank's columns) of rank r's slab, transposed
     # A^T slab: out[i][r*nb + k] = recv[r][i][k]
-    return recv.permute(1, 0, 2).reshape(nb, n).contiguous() if world > 1 else recv.reshape(nb, n)
+    if world == 1:
+        return recv.reshape(nb, n)
+    if tiles and getattr(backend, "reads_tiles", False):
+        return recv
+    return recv.permute(1, 0, 2).reshape(nb, n).contiguous()
 
 
 class SlabBeam2D:
@@ -161,7 +174,7 @@ class SlabBeam2D:
     # forward 2-D transform: field rows -> transposed spectrum columns
     def _fft2(self, field):
         rows = self.backend.lines(field, self.r0)                            # FFT along x
-        cols = exchange_transpose(rows, self.backend, self.group)            # this rank's grid columns, as lines
+        cols = exchange_transpose(rows, self.backend, self.group, tiles=True)  # this rank's grid columns, as lines
         return self.backend.lines(cols, self.r0, transposed=True)            # FFT along y
 
     def propagate(self, z: float, intensity: bool = False):
@@ -171,8 +184,8 @@ class SlabBeam2D:
         self.z += z
         # spectrum *= H (state kept, transposed layout) and inverse transform along y, one local pass
         cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True, z=z, state_out=self.spectrum_t)
-        rows = exchange_transpose(cols, self.backend, self.group)
-        inten = self.backend.empty(*rows.shape, real=True) if intensity else None
+        rows = exchange_transpose(cols, self.backend, self.group, tiles=True)
+        inten = self.backend.empty(*self.field.shape, real=True) if intensity else None
         self.field = self.backend.lines(rows, self.r0, inverse=True, intensity=inten, out=self.field)
         return inten
 

@@ -448,6 +448,27 @@ def test_long_line_kernel_matches_numpy(bits, n, tol):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("bits,n,tile", [(64, 1024, 256), (128, 512, 64), (64, 4096, 512), (64, 32768, 4096), (128, 16384, 8192)])
+def test_pass_lines_tiles_equals_unpacked(bits, n, tile):
+    """lp2d_pass_lines_tiles (the line pass reading the receive buffer of the tile exchange) == lp2d_pass_lines on the
+    unpacked slab, bit for bit, for the single-CTA and the cluster line kernels, with and without H."""
+    from lightprop2d_b200.slab import CudaLineBackend
+    be = CudaLineBackend(200 * lp.um * n / 256, n, 632 * lp.nm, bits)
+    rows, line0 = 6, n // 2 - 3
+    x = torch.randn(rows, n, dtype=torch.complex64 if bits == 64 else torch.complex128, device="cuda")
+    tiles = x.reshape(rows, n // tile, tile).permute(1, 0, 2).contiguous()      # [c][i][k] = x[i][c*tile + k]
+    assert torch.equal(be.lines(tiles, line0), be.lines(x, line0))
+    st0, st1 = torch.empty_like(x), torch.empty_like(x)
+    a = be.lines(x, line0, inverse=True, transposed=True, z=0.013, state_out=st0)
+    b = be.lines(tiles, line0, inverse=True, transposed=True, z=0.013, state_out=st1)
+    assert torch.equal(a, b) and torch.equal(st0, st1)
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.lp2d_pass_lines_tiles(be.plan.handle, _lib.OP_FFT, tiles.data_ptr(), 3, a.data_ptr(), None, None, line0, rows, 0, 0.0, st) == 1
+    assert lib.lp2d_pass_lines_tiles(be.plan.handle, _lib.OP_FFT, tiles.data_ptr(), tile, tiles.data_ptr(), None, None, line0, rows, 0, 0.0, st) == 1
+
+
+@pytest.mark.gpu
 def test_slab_16384_plane_waves():
     """One 16384^2 complex64 grid through the slab path on one GPU (cluster line kernel + transposing
     pack): spectrum support, propagated field and propagate(z); propagate(-z) round trip against the
