@@ -8,12 +8,14 @@ static const XlOps<float> kXlF32[] = {
     Xl<float, 16384, 16, 2>::entry(1),
     Xl<float, 16384, 32, 1>::entry(2),
     Xl<float, 16384, 32, 2>::entry(3),
+    Xl<float, 16384, 32, 4>::entry(4),
     // measured (profiles/r1d_xl_variants.log): E = 32 (two exchanges instead of three) wins at 32768; more CTAs
     // per line lose (a larger share of the exchange crosses SMs)
     Xl<float, 32768, 32, 2>::entry(),
     Xl<float, 32768, 16, 4>::entry(1),
     Xl<float, 32768, 16, 2>::entry(2),
     Xl<float, 32768, 32, 4>::entry(3),
+    Xl<float, 32768, 32, 8>::entry(4),
 };
 static const XlOps<double> kXlF64[] = {
     Xl<double, 8192, 8, 1>::entry(),

@@ -4,10 +4,10 @@
 // shared memory of one CTA next to its Stockham exchange buffer.  Here a line belongs to a
 // cluster of CL CTAs: TPL = N / E threads in total, THREADS = TPL / CL per CTA, thread t (global
 // within the cluster) owns the samples t + TPL * m exactly as in fft_core.cuh, so loads and stores
-// stay HBM <-> registers, coalesced.  The padded exchange buffer of LINE_SLOTS samples is cut in
-// CL contiguous pieces, one per CTA; a scatter / gather goes to whichever CTA holds the slot
-// through distributed shared memory (mapa + ld/st.shared::cluster), and the two barriers of a
-// pass are cluster barriers.  Same pass schedule, same twiddle tables, same arithmetic as the
+// stay HBM <-> registers, coalesced.  The exchange buffer of N samples is spread over the CTAs so
+// that a thread GATHERS only from its own CTA (plain ld.shared); the scatter stores go to whichever
+// CTA will gather the slot, through distributed shared memory (mapa + st.shared::cluster), and the
+// two barriers of a pass are cluster barriers.  Same pass schedule, same twiddle tables, same arithmetic as the
 // single-CTA line kernel (line_pass), so results agree with it to rounding.
 //
 // Used by lp2d_pass_lines (the row pass of the slab-decomposed grid, BASELINE.json config 4:
@@ -55,33 +55,43 @@ struct XlCfg {
     using LP = LinePlan<N, E>;
     static constexpr int TPL = LP::TPL;
     static constexpr int THREADS = TPL / CL;
-    static constexpr int CH = LP::LINE_SLOTS / CL;               // exchange slots held by one CTA
+    static constexpr int CH = N / CL;                            // exchange slots held by one CTA (= E * THREADS)
     static constexpr size_t SMEM = (size_t)CH * sizeof(cx<T>);
     // resident CTAs per SM: registers (2 E sizeof(T)/4 for the data, as many again for the butterflies), shared memory, threads
     static constexpr int REGS = (E * (int)sizeof(T) >= 128) ? 128 : 64;
     static constexpr int MINB_R = 65536 / (THREADS * REGS), MINB_S = (int)((227 * 1024) / (SMEM + 1024)), MINB_T = 2048 / THREADS;
     static constexpr int MINB0 = MINB_R < MINB_S ? (MINB_R < MINB_T ? MINB_R : MINB_T) : (MINB_S < MINB_T ? MINB_S : MINB_T);
     static constexpr int MINB = MINB0 < 1 ? 1 : MINB0;
-    static_assert(TPL % CL == 0 && LP::LINE_SLOTS % CL == 0, "cluster split");
+    static_assert(TPL % CL == 0 && (CL & (CL - 1)) == 0, "cluster split");
     static_assert(THREADS <= 1024 && THREADS % 32 == 0, "block size");
     static_assert(SMEM <= 227 * 1024, "exchange piece does not fit an SM");
     static_assert(CL >= 1 && CL <= 8, "portable cluster size");
 };
 
-// shared::cluster address of exchange slot `slot`
-template <typename T, int CL, int CH>
-__device__ __forceinline__ unsigned xl_addr(const unsigned (&sb)[CL], int slot) {
+// Where sample position g of the line lives between two passes.  The owner is the CTA whose thread
+// GATHERS it (thread t reads t + TPL * m, so owner = (g mod TPL) / THREADS): every gather is a local,
+// conflict-free ld.shared of consecutive slots, and only the scatter stores -- fire and forget -- cross
+// SMs.  Within the owner the slot is (g / TPL) * THREADS + g mod THREADS, XOR-swizzled with the next five
+// bits so that the stride-R scatter of the first pass spreads over the banks (a warp's gather reads 32
+// consecutive slots with those bits constant: the swizzle permutes them among themselves).
+__device__ __forceinline__ int xl_swz(int off) { return off ^ ((off >> 5) & 31); }
+
+template <typename T, int N, int E, int CL>
+__device__ __forceinline__ unsigned xl_scatter_addr(const unsigned (&sb)[CL], int g) {
+    constexpr int TPL = N / E, TH = TPL / CL;
+    const int gm = g & (TPL - 1);
+    const int owner = gm / TH;
+    const int off = (g / TPL) * TH + (gm & (TH - 1));
     unsigned b = sb[0];
-    int off = slot;
 #pragma unroll
     for (int r = 1; r < CL; ++r)
-        if (slot >= r * CH) { b = sb[r]; off = slot - r * CH; }
-    return b + (unsigned)off * (unsigned)sizeof(cx<T>);
+        if (owner == r) b = sb[r];
+    return b + (unsigned)xl_swz(off) * (unsigned)sizeof(cx<T>);
 }
 
 // One Stockham pass (see line_pass in fft_core.cuh) with the exchange in distributed shared memory.
 template <typename T, int N, int E, int CL, int P>
-__device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* __restrict__ tw, int t) {
+__device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* local, const cx<T>* __restrict__ tw, int t) {
     using LP = LinePlan<N, E>;
     using K = XlCfg<T, N, E, CL>;
     constexpr int R = LP::radix(P);
@@ -94,7 +104,7 @@ __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL],
     if (P > 0) {
         xl_sync<CL>();                       // the scatter of the previous pass is visible cluster-wide
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = ClMem<T>::ld(xl_addr<T, CL, K::CH>(sb, LP::pad(t + TPL * m)));
+        for (int m = 0; m < E; ++m) v[m] = local[xl_swz(m * K::THREADS + (int)threadIdx.x)];
     }
     if (!last) xl_sync<CL>();                // everyone has read (and, at P = 0, every CTA of the cluster runs)
 #pragma unroll
@@ -128,15 +138,15 @@ __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL],
         } else {
             const int base = (j / Ns) * (Ns * R) + (j & (Ns - 1));
 #pragma unroll
-            for (int r = 0; r < R; ++r) ClMem<T>::st(xl_addr<T, CL, K::CH>(sb, LP::pad(base + r * Ns)), u[r]);
+            for (int r = 0; r < R; ++r) ClMem<T>::st(xl_scatter_addr<T, N, E, CL>(sb, base + r * Ns), u[r]);
         }
     }
 }
 
 template <typename T, int N, int E, int CL, int P = 0>
-__device__ __forceinline__ void xl_fft(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* tw, int t) {
-    xl_pass<T, N, E, CL, P>(v, sb, tw, t);
-    if constexpr (P + 1 < LinePlan<N, E>::npass()) xl_fft<T, N, E, CL, P + 1>(v, sb, tw, t);
+__device__ __forceinline__ void xl_fft(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* local, const cx<T>* tw, int t) {
+    xl_pass<T, N, E, CL, P>(v, sb, local, tw, t);
+    if constexpr (P + 1 < LinePlan<N, E>::npass()) xl_fft<T, N, E, CL, P + 1>(v, sb, local, tw, t);
 }
 
 // Row pass over lines p.line0 .. p.line0 + p.nlines - 1 (one line per cluster):
@@ -194,7 +204,7 @@ xl_line_kernel(const LineArgs<T> p) {
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
     }
-    xl_fft<T, N, E, CL>(v, sb, p.tw, t);
+    xl_fft<T, N, E, CL>(v, sb, reinterpret_cast<const cx<T>*>(xl_smem), p.tw, t);
     if (inv) {
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
