@@ -34,7 +34,7 @@ def main():
         x = torch.randn(nl, n, dtype=torch.complex64 if bits == 64 else torch.complex128, device="cuda")
         out, st = torch.empty_like(x), torch.empty_like(x)
         ref = None
-        for var in (0, 1, 2, 3, 4):
+        for var in [int(v) for v in (sys.argv[2].split(',') if len(sys.argv) > 2 else '0,1,2,3'.split(','))]:
             os.environ["LP2D_XL_VARIANT"] = str(var)
             be = CudaLineBackend(0.4 * n / 1024, n, 532e-7, bits)
             name = be.plan.step_kernel_name() if hasattr(be.plan, "step_kernel_name") else ""
