@@ -1,7 +1,5 @@
 // Long-line kernel set (cluster / distributed shared memory): (N, E, CTAs per line); LP2D_XL_VARIANT picks
 // an alternative split of the same size (tuning)
-// one line per SM and ~50 instructions per sample and pass: these kernels are issue bound -> packed f32x2 complex arithmetic
-#define LP2D_PACKED_F32 1
 #include "xl_line.cuh"
 
 namespace lp2d {
@@ -11,15 +9,14 @@ static const XlOps<float> kXlF32[] = {
     Xl<float, 16384, 32, 1>::entry(2),
     Xl<float, 16384, 32, 2>::entry(3),
     Xl<float, 16384, 32, 4>::entry(4),
-    Xl<float, 16384, 32, 1, 1>::entry(5),
-    // measured (profiles/r1d_xl_variants.log): E = 32 (two exchanges instead of three) wins at 32768; more CTAs
-    // per line lose (a larger share of the exchange crosses SMs)
+    // measured (profiles/r1d_xl_variants*.log): E = 32 (two exchanges instead of three) wins at 32768; more CTAs
+    // per line lose (a larger share of the exchange crosses SMs); packed f32x2 arithmetic and two-level
+    // twiddles change nothing (r1d_xl_packed_tw2.log): the phases of the one resident line are serialised
     Xl<float, 32768, 32, 2>::entry(),
     Xl<float, 32768, 16, 4>::entry(1),
     Xl<float, 32768, 16, 2>::entry(2),
     Xl<float, 32768, 32, 4>::entry(3),
     Xl<float, 32768, 32, 8>::entry(4),
-    Xl<float, 32768, 32, 2, 1>::entry(5),
 };
 static const XlOps<double> kXlF64[] = {
     Xl<double, 8192, 8, 1>::entry(),

@@ -90,7 +90,7 @@ __device__ __forceinline__ unsigned xl_scatter_addr(const unsigned (&sb)[CL], in
 }
 
 // One Stockham pass (see line_pass in fft_core.cuh) with the exchange in distributed shared memory.
-template <typename T, int N, int E, int CL, int TW2, int P>
+template <typename T, int N, int E, int CL, int P>
 __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* local, const cx<T>* __restrict__ tw, int t) {
     using LP = LinePlan<N, E>;
     using K = XlCfg<T, N, E, CL>;
@@ -115,20 +115,7 @@ __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL],
         for (int r = 0; r < R; ++r) u[r] = v[q + r * Q];
         if (Ns > 1) {
             const int k = j & (Ns - 1);
-            if constexpr (R > 16 && TW2) {
-                // radix 32: w^(k r) = w^(4a k) * w^(b k), r = 4a + b: 10 table loads instead of 31 (the table of the
-                // last pass is larger than what is left of L1 next to the exchange buffer: twiddle loads are L2 traffic)
-                cx<T> wb[3], wa[7];
-#pragma unroll
-                for (int b = 1; b < 4; ++b) wb[b - 1] = __ldg(&tw[twoff + (b - 1) * Ns + k]);
-#pragma unroll
-                for (int a = 1; a < 8; ++a) wa[a - 1] = __ldg(&tw[twoff + (4 * a - 1) * Ns + k]);
-#pragma unroll
-                for (int r = 1; r < R; ++r) {
-                    if ((r >> 2) > 0) u[r] = cmul(u[r], wa[(r >> 2) - 1]);
-                    if ((r & 3) > 0) u[r] = cmul(u[r], wb[(r & 3) - 1]);
-                }
-            } else if constexpr (R > 16) {
+            if constexpr (R > 16) {
                 // radix 32: load and apply the twiddles eight at a time (register pressure, see line_pass)
 #pragma unroll
                 for (int r0 = 1; r0 < R; r0 += 8) {
@@ -156,16 +143,16 @@ __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL],
     }
 }
 
-template <typename T, int N, int E, int CL, int TW2, int P = 0>
+template <typename T, int N, int E, int CL, int P = 0>
 __device__ __forceinline__ void xl_fft(cx<T> (&v)[E], const unsigned (&sb)[CL], const cx<T>* local, const cx<T>* tw, int t) {
-    xl_pass<T, N, E, CL, TW2, P>(v, sb, local, tw, t);
-    if constexpr (P + 1 < LinePlan<N, E>::npass()) xl_fft<T, N, E, CL, TW2, P + 1>(v, sb, local, tw, t);
+    xl_pass<T, N, E, CL, P>(v, sb, local, tw, t);
+    if constexpr (P + 1 < LinePlan<N, E>::npass()) xl_fft<T, N, E, CL, P + 1>(v, sb, local, tw, t);
 }
 
 // Row pass over lines p.line0 .. p.line0 + p.nlines - 1 (one line per cluster):
 //   load -> [transfer function H, computed per sample in FP64] -> [store state] -> (i)FFT -> scale
 //        -> [store] [store |.|^2]
-template <typename T, int N, int E, int CL, int PRE, int TW2>
+template <typename T, int N, int E, int CL, int PRE>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(XlCfg<T, N, E, CL>::THREADS, XlCfg<T, N, E, CL>::MINB)
 xl_line_kernel(const LineArgs<T> p) {
     using K = XlCfg<T, N, E, CL>;
@@ -217,7 +204,7 @@ xl_line_kernel(const LineArgs<T> p) {
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
     }
-    xl_fft<T, N, E, CL, TW2>(v, sb, reinterpret_cast<const cx<T>*>(xl_smem), p.tw, t);
+    xl_fft<T, N, E, CL>(v, sb, reinterpret_cast<const cx<T>*>(xl_smem), p.tw, t);
     if (inv) {
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = cswap(v[m]);
@@ -247,13 +234,13 @@ struct XlOps {
     void (*twiddles)(std::vector<double>& re_im);
 };
 
-template <typename T, int N, int E, int CL, int TW2 = 0>
+template <typename T, int N, int E, int CL>
 struct Xl {
     using LP = LinePlan<N, E>;
     using K = XlCfg<T, N, E, CL>;
     template <int PRE>
     static cudaError_t go(const LineArgs<T>& a, cudaStream_t s) {
-        xl_line_kernel<T, N, E, CL, PRE, TW2><<<(unsigned)a.nlines * CL, K::THREADS, K::SMEM, s>>>(a);
+        xl_line_kernel<T, N, E, CL, PRE><<<(unsigned)a.nlines * CL, K::THREADS, K::SMEM, s>>>(a);
         ++g_launches;
         return cudaGetLastError();
     }
@@ -261,9 +248,9 @@ struct Xl {
         return pre == PRE_H ? go<PRE_H>(a, s) : pre == PRE_NONE ? go<PRE_NONE>(a, s) : cudaErrorInvalidValue;
     }
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(xl_line_kernel<T, N, E, CL, PRE_NONE, TW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(xl_line_kernel<T, N, E, CL, PRE_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(xl_line_kernel<T, N, E, CL, PRE_H, TW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+        return cudaFuncSetAttribute(xl_line_kernel<T, N, E, CL, PRE_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
     }
     // same table layout as Ops::twiddles (sizes.cuh)
     static void twiddles(std::vector<double>& w) {
