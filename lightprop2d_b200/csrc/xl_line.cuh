@@ -49,6 +49,16 @@ __device__ __forceinline__ void xl_sync() {
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 }
+// Rendezvous without memory ordering: before the first scatter of a line there is nothing to publish (the barrier
+// only makes sure every CTA of the cluster is running), and a release here would wait for the state stores to HBM.
+template <int CL>
+__device__ __forceinline__ void xl_rendezvous() {
+    if (CL == 1) {
+        __syncthreads();
+    } else {
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+    }
+}
 
 template <typename T, int N, int E, int CL>
 struct XlCfg {
@@ -106,7 +116,10 @@ __device__ __forceinline__ void xl_pass(cx<T> (&v)[E], const unsigned (&sb)[CL],
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = local[xl_swz(m * K::THREADS + (int)threadIdx.x)];
     }
-    if (!last) xl_sync<CL>();                // everyone has read (and, at P = 0, every CTA of the cluster runs)
+    if (!last) {
+        if (P == 0) xl_rendezvous<CL>();     // every CTA of the cluster runs
+        else xl_sync<CL>();                  // everyone has read its inputs before anyone overwrites the exchange buffer
+    }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         const int j = t + TPL * q;
@@ -222,8 +235,8 @@ xl_line_kernel(const LineArgs<T> p) {
 #pragma unroll
         for (int m = 0; m < E; ++m) __stcs(&p.inten[base + t + TPL * m], v[m].x * v[m].x + v[m].y * v[m].y);
     }
-    // no CTA may exit while a peer can still gather from its shared memory
-    if (CL > 1) xl_sync<CL>();
+    // no barrier at the end: gathers are local, and the last scatter into this CTA's shared memory was
+    // published by the barrier before the final gather (a release here would hold the SM until the stores drain)
 }
 
 template <typename T>
