@@ -90,8 +90,10 @@ struct lp2d_plan {
     int num_sms;
     void* ring;                // L2-resident intermediate planes
     long long ring_bytes;
-    unsigned int* counters;    // work queue head + per-(stage, group) completion counters
-    int counters_cap;
+    unsigned int* counters;    // two sets of: work queue head + per-(stage, group) completion counters; launches
+    int counters_cap;          // alternate between the sets and zero what the previous launch used
+    int counter_set;           // set the next fused launch uses
+    int counters_used[2];      // entries the last launch on each set dirtied
     int pipe_g, pipe_lag, pipe_slots;   // tuning overrides (0 = automatic)
     int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
     int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
@@ -229,6 +231,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         return cuda_fail(e, "cudaMemcpy(tables)");
     }
     p->ring = nullptr; p->counters = nullptr; p->ring_bytes = 0; p->counters_cap = 0; p->num_sms = 0;
+    p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -248,9 +251,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
             p->counters_cap = 1 + P2_MAX_STAGES * 16384;
             if (e == cudaSuccess) e = cudaMalloc(&p->ring, (size_t)ring_bytes);
-            if (e == cudaSuccess) e = cudaMalloc(&p->counters, sizeof(unsigned int) * (p->counters_cap + 1));
-            // zeroed once: every launch leaves the counters it used zeroed (t3_kernel)
-            if (e == cudaSuccess) e = cudaMemset(p->counters, 0, sizeof(unsigned int) * (p->counters_cap + 1));
+            if (e == cudaSuccess) e = cudaMalloc(&p->counters, 2 * sizeof(unsigned int) * p->counters_cap);
+            // zeroed once: every launch zeroes what the previous launch of the plan used (t3_kernel)
+            if (e == cudaSuccess) e = cudaMemset(p->counters, 0, 2 * sizeof(unsigned int) * p->counters_cap);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_tw, n2 * csz);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_fac, (size_t)n * (q32 ? q32->fl : q64->fl) * csz);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->p2_done, cudaEventDisableTiming);
@@ -441,7 +444,9 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.ring = static_cast<cx<T>*>(p->ring);
         a.tw = static_cast<const cx<T>*>(p->p2_tw);
         a.fac = static_cast<const cx<T>*>(p->p2_fac);
-        a.counters = p->counters;
+        a.counters = p->counters + (size_t)p->counter_set * p->counters_cap;
+        a.zero_counters = p->counters + (size_t)(p->counter_set ^ 1) * p->counters_cap;
+        a.zero_count = p->counters_used[p->counter_set ^ 1];
         a.nbeams = nb;
         a.nstages = nstages;
         a.ngroups = (int)((nb + G - 1) / G);
@@ -461,6 +466,9 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.total_items = (int)total;
         const unsigned grid = (unsigned)total;      // one CTA per item
         LP2D_CU(ops->launch(a, grid, need_factor, s, p->ring, p->pipe_persist ? (size_t)(slots * G * plane) : 0), "fused step launch");
+        p->counters_used[p->counter_set ^ 1] = 0;
+        p->counters_used[p->counter_set] = 1 + nstages * a.ngroups;
+        p->counter_set ^= 1;
     }
     return LP2D_OK;
 }

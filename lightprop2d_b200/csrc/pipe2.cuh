@@ -63,7 +63,9 @@ struct P2Args {
     cx<T>* ring;              // ring_slots * G planes
     const cx<T>* tw;          // twiddles of LinePlan<N, E>
     const cx<T>* fac;         // factor plane [N lines][FL], folded (P2_MAP_*)
-    unsigned int* counters;   // [0] next item; [1 + s*ngroups + g] completed items of (s, g); then CTAs that have exited
+    unsigned int* counters;   // [0] next item; [1 + s*ngroups + g] completed items of (s, g); all zero at launch
+    unsigned int* zero_counters;   // the counter set the PREVIOUS launch of the plan used: zeroed by this launch (the plan
+    int zero_count;                // alternates between two sets, so no CTA has to find out that it is the last one)
     long long nbeams;
     int nstages, ngroups, G, lag, ring_slots, total_items, fac_map;
     int hints;                // P2_HINT_*
@@ -81,6 +83,12 @@ __device__ __forceinline__ unsigned int p2_ld_relaxed(const unsigned int* ctr) {
 }
 __device__ __forceinline__ void p2_signal(unsigned int* ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+// completion of a FINAL-stage item: the counter only tells the stage that refills the ring slot that the slot has
+// been read (the loads completed before the item's stores were issued); nobody inside the launch reads what the item
+// stored, so there is nothing to release and the CTA does not wait for its stores to drain
+__device__ __forceinline__ void p2_signal_consumed(unsigned int* ctr) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
 enum { P2_HINT_KEEP_RING = 2 };      // bit 0 was the (dropped) hint on the cp.async path
@@ -415,6 +423,9 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     uint32_t tma_parity = 0;
+    // zero the counter set of the previous launch (fire and forget; it is next used by the launch after this one)
+    for (unsigned int i = blockIdx.x * K::THREADS + tid; i < (unsigned int)p.zero_count; i += gridDim.x * K::THREADS)
+        p.zero_counters[i] = 0u;
     if (tid == 0) {
         if (p.use_tma) p2_mbar_init(&s_bar, 1);
         const int drawn = (int)atomicAdd(&p.counters[0], 1u);
@@ -444,21 +455,14 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
             t3_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
         }
         __syncthreads();                                   // all stores of the item are issued
-        if (tid == 0) p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+        if (tid == 0) {
+            if (it.s == p.nstages - 1) p2_signal_consumed(p.counters + 1 + it.s * p.ngroups + it.g);
+            else p2_signal(p.counters + 1 + it.s * p.ngroups + it.g);
+        }
     }
-    // The CTA that finishes last leaves the counters zeroed for the next launch (no memset per step):
-    // every CTA counts itself out after its last access to the counters; whoever brings the count to the
-    // grid size knows that nobody reads them any more.
-    if (tid == 0) {
-        const unsigned int ncnt = 1u + (unsigned)p.nstages * (unsigned)p.ngroups;       // index of the exit counter
-        __threadfence();
-        s_item = (atomicAdd(&p.counters[ncnt], 1u) == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_item) {
-        const unsigned int ncnt = 1u + (unsigned)p.nstages * (unsigned)p.ngroups;
-        for (unsigned int i = tid; i <= ncnt; i += K::THREADS) p.counters[i] = 0u;
-    }
+    // No exit protocol: the counters this launch dirties are zeroed by the NEXT launch of the plan (see above), so a
+    // CTA leaves as soon as its signal is issued (an "am I the last CTA" atomic kept all eight warps at a barrier
+    // for a fence + an L2 round trip: 18 % of the warp time in profiles/r1c_ncu_full_t3_default_summary.txt).
 }
 
 // The factor plane: fac[line][idx], idx = 0 .. N/2 (row stride FL).

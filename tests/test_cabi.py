@@ -32,6 +32,9 @@ def test_version_and_limits():
     assert lib.lp2d_version() == 100
     assert lib.lp2d_min_npoints() == 16
     assert lib.lp2d_max_npoints(_lib.C64) >= 4096 and lib.lp2d_max_npoints(_lib.C128) >= 4096
+    # BASELINE.json config 4: lines of a 32768^2 grid (cluster line kernel, slab path)
+    assert lib.lp2d_max_line_points(_lib.C64) >= 32768 and lib.lp2d_max_line_points(_lib.C128) >= 32768
+    assert lib.lp2d_pass_lines_tiles(None, 0, None, 4, None, None, None, 0, 0, 0, 0.0, None) == 1     # NULL plan
 
 
 @pytest.mark.parametrize("case", range(6))
