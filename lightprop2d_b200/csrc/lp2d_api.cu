@@ -276,7 +276,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_LAG");   p->pipe_lag = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_SLOTS"); p->pipe_slots = env ? atoi(env) : 0;
-    env = getenv("LP2D_PIPE_HINTS"); p->pipe_hints = env ? atoi(env) : 3;
+    // bit 1: evict-last ring stores; bit 2: speculative L2 prefetch of the first-stage rows (-1: for two-stage steps only,
+    // where it is worth 2 %; it costs 5 % in the three-stage chain at 512, profiles/r1d_pipe_sweep.log)
+    env = getenv("LP2D_PIPE_HINTS"); p->pipe_hints = env ? atoi(env) : -1;
     // measured (profiles/r1c_size_sweep.log): the fused kernel wins on the steps that read AND write state
     // (3*P*B algorithmic bytes); plain fft2 and the three-stage fresh chain stay on the per-pass kernels
     // and, for the small planes, on more of them (profiles/r1c_size_sweep.log, r1c_group_sweep.log):
@@ -452,7 +454,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.ngroups = (int)((nb + G - 1) / G);
         a.G = (int)G; a.lag = lag; a.ring_slots = slots;
         a.fac_map = fac_kind == P2_FAC_LENS ? P2_MAP_CENTRE : P2_MAP_FREQ;
-        a.hints = p->pipe_hints;
+        a.hints = p->pipe_hints >= 0 ? p->pipe_hints : (P2_HINT_KEEP_RING | 1 | (nstages == 2 ? P2_HINT_PREFETCH : 0));
         a.use_tma = 0;
         if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && a.st[1].out != nullptr &&
             (ops->w * (int)sizeof(cx<T>)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.st[1].out) & 15) == 0) {

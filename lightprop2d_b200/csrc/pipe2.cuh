@@ -91,7 +91,8 @@ __device__ __forceinline__ void p2_signal_consumed(unsigned int* ctr) {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
-enum { P2_HINT_KEEP_RING = 2 };      // bit 0 was the (dropped) hint on the cp.async path
+enum { P2_HINT_KEEP_RING = 2,        // bit 0 was the (dropped) hint on the cp.async path
+       P2_HINT_PREFETCH = 4 };       // speculative L2 prefetch of the user rows of item blockIdx.x while the ticket is drawn
 // KIND is a compile-time value: a policy selected at run time ends up in a misaligned uniform
 // register pair (ptxas 12.9) and the copy traps as an illegal instruction.
 template <int KIND>     // 0 no hint, 1 evict first, 2 evict last
@@ -423,6 +424,18 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     uint32_t tma_parity = 0;
+    // Tickets are drawn (almost) in block order: block k will most likely get item k, and if not, a CTA that starts at
+    // the same time will.  While the ticket and the dependency check are in flight (two L2 round trips), ask L2 for
+    // the user rows of a first-stage item, so that the loads of whoever works on it find them there.
+    if ((p.hints & P2_HINT_PREFETCH) && tid < W * p.G && (int)blockIdx.x < p.total_items) {
+        P2Item gi;
+        if (p2_decode<T, K::TILES>(p, (int)blockIdx.x, gi) && gi.s == 0 && !p.st[0].in_ring) {
+            const long long b = (long long)gi.g * p.G + tid / W;
+            const cx<T>* row = p.st[0].in + b * ((long long)N * N) + (long long)(gi.tile * W + tid % W) * N;
+            if (b < p.nbeams && (reinterpret_cast<uintptr_t>(row) & 15) == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"((unsigned)(N * sizeof(cx<T>))) : "memory");
+        }
+    }
     // zero the counter set of the previous launch (fire and forget; it is next used by the launch after this one)
     for (unsigned int i = blockIdx.x * K::THREADS + tid; i < (unsigned int)p.zero_count; i += gridDim.x * K::THREADS)
         p.zero_counters[i] = 0u;
