@@ -424,6 +424,11 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     uint32_t tma_parity = 0;
+    unsigned int drawn = 0u;
+    if (tid == 0) {                                        // first thing: the ticket (its latency covers what follows)
+        if (p.use_tma) p2_mbar_init(&s_bar, 1);
+        drawn = atomicAdd(&p.counters[0], 1u);
+    }
     // Tickets are drawn (almost) in block order: block k will most likely get item k, and if not, a CTA that starts at
     // the same time will.  While the ticket and the dependency check are in flight (two L2 round trips), ask L2 for
     // the user rows of a first-stage item, so that the loads of whoever works on it find them there.
@@ -439,15 +444,32 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     // zero the counter set of the previous launch (fire and forget; it is next used by the launch after this one)
     for (unsigned int i = blockIdx.x * K::THREADS + tid; i < (unsigned int)p.zero_count; i += gridDim.x * K::THREADS)
         p.zero_counters[i] = 0u;
-    if (tid == 0) {
-        if (p.use_tma) p2_mbar_init(&s_bar, 1);
-        const int drawn = (int)atomicAdd(&p.counters[0], 1u);
-        P2Item it0;
-        if (drawn < p.total_items && p2_decode<T, K::TILES>(p, drawn, it0)) {
-            p2_wait_ready<T, K::TILES>(p, drawn, (unsigned)K::TILES);
-            s_item = drawn;
-        } else {
-            s_item = -1;                                   // fill / drain item of the schedule: nothing to do
+    // While the ticket atomic of lane 0 is in flight, lane 1 checks the dependencies of the item
+    // the CTA will most likely get (item blockIdx.x: tickets are drawn almost in block order, and the dependencies are
+    // per (stage, group), which 128 neighbouring items share).  If the ticket turns out to belong to the same (stage,
+    // group) and the check found it complete, the second L2 round trip is skipped; otherwise the normal wait runs.
+    if (tid < 32) {
+        unsigned int spec = 0u;
+        int gs = -1, gg = -1;
+        if (tid == 1 && (int)blockIdx.x < p.total_items) {
+            P2Item gi;
+            if (p2_decode<T, K::TILES>(p, (int)blockIdx.x, gi)) {
+                gs = gi.s; gg = gi.g;
+                spec = p2_ready<T, K::TILES>(p, (int)blockIdx.x, (unsigned)K::TILES) ? 1u : 0u;
+            }
+        }
+        drawn = __shfl_sync(0xffffffffu, drawn, 0);
+        spec = __shfl_sync(0xffffffffu, spec, 1);
+        gs = __shfl_sync(0xffffffffu, gs, 1);
+        gg = __shfl_sync(0xffffffffu, gg, 1);
+        if (tid == 0) {
+            P2Item it0;
+            if ((int)drawn < p.total_items && p2_decode<T, K::TILES>(p, (int)drawn, it0)) {
+                if (!(spec != 0u && it0.s == gs && it0.g == gg)) p2_wait_ready<T, K::TILES>(p, (int)drawn, (unsigned)K::TILES);
+                s_item = (int)drawn;
+            } else {
+                s_item = -1;                               // fill / drain item of the schedule: nothing to do
+            }
         }
     }
     __syncthreads();
