@@ -403,7 +403,8 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     // lag (in groups) between consecutive stages of a group: the items in between cover every resident
     // CTA (with a margin), so that what an item depends on was drawn more than a wave earlier
     const long long reach = (5 * conc) / 4;
-    int lag = p->pipe_lag > 0 ? p->pipe_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles));
+    // three-stage chains: one more group of slack (measured at 512: 2.47 -> 2.36 us/beam, profiles/r1d_pipe_sweep512.log)
+    int lag = p->pipe_lag > 0 ? p->pipe_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles)) + (nstages == 3 ? 1 : 0);
     if (lag < 1) lag = 1;
     // ring slots (groups): the stage that refills a slot must also be `lag` groups behind the last
     // stage of the group that held it
