@@ -68,8 +68,11 @@ class _NumpyLineBackend:
     the transfer function from the oracle's expressions, CPU torch tensors (so that gloo can move them).
     Exercises the partitioning / exchange / orientation logic of SlabBeam2D without a GPU."""
 
-    def __init__(self, area_size, npoints, wl, complex_bits):
+    def __init__(self, area_size, npoints, wl, complex_bits, reads_tiles=False):
         from oracle import beam_oracle as orc
+        # True: lines() is handed the (G, rows, tile) receive buffer of the exchange, as the CUDA backend is
+        # (lp2d_pass_lines_tiles); False: SlabBeam2D unpacks it with a strided copy first
+        self.reads_tiles = reads_tiles
         self.n = npoints
         self.g = orc.make_grids(area_size, npoints, wl)
         self.npc = np.complex64 if complex_bits == 64 else np.complex128
@@ -80,6 +83,9 @@ class _NumpyLineBackend:
         return torch.empty(*shape, dtype=self.rdtype if real else self.cdtype)
 
     def lines(self, x, line0, inverse=False, transposed=False, z=None, state_out=None, intensity=None, out=None):
+        if x.dim() == 3:                            # tiles [c][i][k] = slab[i][c*tile + k] (include/lp2d.h, lp2d_pass_lines_tiles)
+            assert self.reads_tiles
+            x = x.permute(1, 0, 2).reshape(x.shape[1], -1)
         a = x.numpy().copy()
         rows = a.shape[0]
         if z is not None:
@@ -105,7 +111,7 @@ class _NumpyLineBackend:
         return x.reshape(rows, ld // tile, tile).permute(1, 2, 0).contiguous()
 
 
-def _slab_worker(rank, world, port, n, bits, q):
+def _slab_worker(rank, world, port, n, bits, q, reads_tiles=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -116,7 +122,7 @@ def _slab_worker(rank, world, port, n, bits, q):
         full = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64 if bits == 64 else np.complex128)
         r0, r1 = slab_rows(n, rank, world)
         b = SlabBeam2D(area, n, wl, init_field=full[r0:r1].copy(), complex_bits=bits,
-                       backend=_NumpyLineBackend(area, n, wl, bits))
+                       backend=_NumpyLineBackend(area, n, wl, bits, reads_tiles))
         spec0 = b.gather_spectrum().numpy()
         inten = b.propagate(z1, intensity=True)
         b.propagate(z2)
@@ -129,13 +135,18 @@ def _slab_worker(rank, world, port, n, bits, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_slab_matches_oracle():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("reads_tiles", [False, True])
+def test_two_rank_slab_matches_oracle(reads_tiles):
+    """Both forms of the exchange: unpacked slab, and the receive buffer handed to the line pass as tiles."""
     from oracle import beam_oracle as orc
     world, n, bits = 2, 64, 128
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, bits, q)) for r in range(world)]
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, bits, q, reads_tiles)) for r in range(world)]
     for p in procs:
         p.start()
     full, spec0, fld, spec, inten0, z = q.get(timeout=180)
