@@ -360,23 +360,30 @@ class Beam2D:
         """beam2d.py:385-404: grow the area at constant dL with edge-replicated samples."""
         torch = _torch()
         old_npoints = self.npoints
-        self.npoints = int(self.npoints * area_size / self.area_size)
-        self.npoints -= self.npoints % 2
-        self.area_size = area_size
-        d_npoints = (self.npoints - old_npoints) // 2
+        npoints = int(self.npoints * area_size / self.area_size)
+        npoints -= npoints % 2
+        d_npoints = (npoints - old_npoints) // 2
+        # validate before any attribute changes: a caught exception must leave the beam as it was
         if d_npoints < 0:
             raise ValueError("count < 0")              # numpy.repeat with a negative count
         n_arr = old_npoints + 2 * d_npoints            # size of the array the reference builds
-        self._construct_grids()
+        if n_arr != npoints:
+            # latent reference bug (odd difference): the array and npoints disagree; the
+            # reference's fft2 then runs on the array size.  Not reproducible with one plan.
+            raise NotImplementedError("expand: npoints difference is odd; array and grid sizes disagree")
+        saved = (self.npoints, self.area_size)
+        self.npoints, self.area_size = npoints, area_size
+        try:
+            self._construct_grids()
+            self._new_plan()
+        except Exception:
+            self.npoints, self.area_size = saved
+            self._construct_grids()
+            raise
         out = torch.empty(*self._f.shape[:-2], n_arr, n_arr, dtype=self._cdtype, device=self._tdev)
         self._call("lp2d_expand", _lib.C64 if self.complex_bits == 64 else _lib.C128, self._f.data_ptr(),
                    out.data_ptr(), old_npoints, n_arr, self._batch(), self._stream())
         self._f = out
-        if n_arr != self.npoints:
-            # latent reference bug (odd difference): the array and npoints disagree; the
-            # reference's fft2 then runs on the array size.  Not reproducible with one plan.
-            raise NotImplementedError("expand: npoints difference is odd; array and grid sizes disagree")
-        self._new_plan()
         self._s = None
 
     def crop(self, area_size: float, npoints: int = 0):
@@ -388,16 +395,22 @@ class Beam2D:
         """beam2d.py:454-460: npoints //= m, block mean of the field, fft2."""
         torch = _torch()
         old = self.npoints
-        self.npoints //= mean_order
-        self._construct_grids()
-        if self.npoints * mean_order != old:
+        npoints = old // mean_order
+        if npoints * mean_order != old:
             raise ValueError(f"cannot reshape array of size {old * old} into shape "
-                             f"({self.npoints},{mean_order},{self.npoints},{mean_order})")
+                             f"({npoints},{mean_order},{npoints},{mean_order})")
+        self.npoints = npoints
+        try:
+            self._construct_grids()
+            self._new_plan()
+        except Exception:
+            self.npoints = old
+            self._construct_grids()
+            raise
         out = torch.empty(*self._f.shape[:-2], self.npoints, self.npoints, dtype=self._cdtype, device=self._tdev)
         self._call("lp2d_coarse", _lib.C64 if self.complex_bits == 64 else _lib.C128, self._f.data_ptr(),
                    out.data_ptr(), old, int(mean_order), self._batch(), self._stream())
         self._f = out
-        self._new_plan()
         self._s = None
 
     def lens_image(self, f: float, l1: float, l2: float):

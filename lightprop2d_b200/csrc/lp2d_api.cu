@@ -107,6 +107,9 @@ struct lp2d_plan {
     void* p2_tw;               // twiddles of the P2 (N, E) schedule
     void* p2_fac;              // factor plane [n][fl]
     int fac_kind, fac_by_column;   // what p2_fac currently holds (0 = nothing)
+    int fac_full;              // ... stored unfolded (lens on a grid whose X^2 is not even around n/2)
+    bool x2_even;              // x2[n/2 - k] == x2[n/2 + k] bit for bit (false after a generator shifted X in place)
+    bool h_even;               // a[k] == a[n - k] and b[k] == b[n - k] bit for bit (the fold of the H plane)
     double fac_p0, fac_p1;
     cudaEvent_t p2_done;       // the ring, the counters and the factor plane are plan state: fused launches of one
     cudaStream_t p2_stream;    // plan are serialised across streams (event recorded on the old stream at a switch)
@@ -231,6 +234,13 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         return cuda_fail(e, "cudaMemcpy(tables)");
     }
     p->ring = nullptr; p->counters = nullptr; p->ring_bytes = 0; p->counters_cap = 0; p->num_sms = 0;
+    // the folds of the factor plane are only valid for tables that are even bit for bit: the reference's
+    // gaussian_beam(x0, y0 != 0) shifts X in place (profiles.py:69-70), slab plans pass swapped tables
+    p->x2_even = true; p->h_even = true; p->fac_full = 0;
+    for (int k = 1; k < n / 2; ++k) {
+        if (host_x2[n / 2 - k] != host_x2[n / 2 + k]) p->x2_even = false;
+        if (host_a[k] != host_a[n - k] || host_b[k] != host_b[n - k]) p->h_even = false;
+    }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
@@ -255,7 +265,8 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             // zeroed once: every launch zeroes what the previous launch of the plan used (t3_kernel)
             if (e == cudaSuccess) e = cudaMemset(p->counters, 0, 2 * sizeof(unsigned int) * p->counters_cap);
             if (e == cudaSuccess) e = cudaMalloc(&p->p2_tw, n2 * csz);
-            if (e == cudaSuccess) e = cudaMalloc(&p->p2_fac, (size_t)n * (q32 ? q32->fl : q64->fl) * csz);
+            // room for an unfolded plane (row stride n) when X^2 is not even
+            if (e == cudaSuccess) e = cudaMalloc(&p->p2_fac, (size_t)n * (size_t)(p->x2_even ? (q32 ? q32->fl : q64->fl) : n + 2) * csz);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->p2_done, cudaEventDisableTiming);
             if (e == cudaSuccess) {
                 if (dtype == LP2D_C64) {
@@ -299,6 +310,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             if (getenv("LP2D_VERBOSE")) fprintf(stderr, "[lp2d] L2 %d MB, persisting max %d MB, set %zu MB\n", prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, want >> 20);
         }
     }
+    // the tables, twiddles and counters were written on the legacy default stream: user streams (non-blocking
+    // ones too) must find them complete
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) { lp2d_plan_destroy(p); return cuda_fail(e, "plan_create: synchronise"); }
     *out = p;
     return LP2D_OK;
 }
@@ -369,17 +383,19 @@ template <> const P2Ops<double>* p2_of<double>(const lp2d_plan* p) { return p->p
 // (a z-sweep with a constant step reuses it for every call).
 template <typename T>
 int p2_ensure_factor(lp2d_plan* p, int kind, int by_column, double p0, double p1, cudaStream_t s) {
-    if (p->fac_kind == kind && p->fac_by_column == by_column && p->fac_p0 == p0 && p->fac_p1 == p1) return LP2D_OK;
+    const int full = (kind == P2_FAC_LENS && !p->x2_even) ? 1 : 0;
+    if (p->fac_kind == kind && p->fac_by_column == by_column && p->fac_full == full && p->fac_p0 == p0 && p->fac_p1 == p1) return LP2D_OK;
     const P2Ops<T>* ops = p2_of<T>(p);
+    const int fl = full ? p->n : ops->fl;
     cudaError_t e;
     if (sizeof(T) == 4)
-        e = p2_factor_plane_f32(static_cast<float2*>(p->p2_fac), p->tabs, p->n, ops->fl, kind, by_column,
+        e = p2_factor_plane_f32(static_cast<float2*>(p->p2_fac), p->tabs, p->n, fl, kind, by_column, full,
                                 kind == P2_FAC_H ? p0 : 0.0, kind == P2_FAC_LENS ? p0 : 0.0, kind == P2_FAC_LENS ? p1 : 0.0, s);
     else
-        e = p2_factor_plane_f64(static_cast<double2*>(p->p2_fac), p->tabs, p->n, ops->fl, kind, by_column,
+        e = p2_factor_plane_f64(static_cast<double2*>(p->p2_fac), p->tabs, p->n, fl, kind, by_column, full,
                                 kind == P2_FAC_H ? p0 : 0.0, kind == P2_FAC_LENS ? p0 : 0.0, kind == P2_FAC_LENS ? p1 : 0.0, s);
     if (e != cudaSuccess) return cuda_fail(e, "factor plane launch");
-    p->fac_kind = kind; p->fac_by_column = by_column; p->fac_p0 = p0; p->fac_p1 = p1;
+    p->fac_kind = kind; p->fac_by_column = by_column; p->fac_full = full; p->fac_p0 = p0; p->fac_p1 = p1;
     return LP2D_OK;
 }
 
@@ -391,6 +407,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
            long long batch, cudaStream_t s) {
     const P2Ops<T>* ops = p2_of<T>(p);
     if (ops == nullptr) return -1;
+    if (fac_kind == P2_FAC_H && !p->h_even) return -1;      // the folded H plane needs even tables: one kernel per pass
     const bool need_factor = fac_kind != P2_FAC_NONE;
     const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
     const int ctas = need_factor ? p->p2_ctas_factor : p->p2_ctas_plain;
@@ -454,7 +471,8 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.nstages = nstages;
         a.ngroups = (int)((nb + G - 1) / G);
         a.G = (int)G; a.lag = lag; a.ring_slots = slots;
-        a.fac_map = fac_kind == P2_FAC_LENS ? P2_MAP_CENTRE : P2_MAP_FREQ;
+        a.fac_map = fac_kind == P2_FAC_LENS ? (p->x2_even ? P2_MAP_CENTRE : P2_MAP_FULL) : P2_MAP_FREQ;
+        a.fac_stride = (fac_kind == P2_FAC_LENS && !p->x2_even) ? p->n : ops->fl;
         a.hints = p->pipe_hints >= 0 ? p->pipe_hints : (P2_HINT_KEEP_RING | 1 | (nstages == 2 ? P2_HINT_PREFETCH : 0));
         a.use_tma = 0;
         if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && a.st[1].out != nullptr &&

@@ -18,9 +18,9 @@ const P2Ops<double>* find_p2_f64(int n, int variant) {
     }
     return first;
 }
-cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl, int kind, int by_column, int full, double z,
                                 double k0, double two_f, cudaStream_t s) {
-    factor_plane_kernel<double><<<148 * 4, 256, 0, s>>>(fac, tabs, tabs + n, tabs + 2 * n, n, fl, kind, by_column, z, k0, two_f);
+    factor_plane_kernel<double><<<148 * 4, 256, 0, s>>>(fac, tabs, tabs + n, tabs + 2 * n, n, fl, kind, by_column, full, z, k0, two_f);
     ++g_launches;
     return cudaGetLastError();
 }

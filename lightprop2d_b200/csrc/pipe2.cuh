@@ -37,7 +37,9 @@ enum { P2_FAC_NONE = 0, P2_FAC_H = 1, P2_FAC_LENS = 2 };
 enum { P2_MAX_STAGES = 3 };
 // how a line position maps to the folded factor row: H is even in kx (index min(pos, N - pos)),
 // the lens phase is even in x around the grid centre (index |pos - N/2|)
-enum { P2_MAP_FREQ = 0, P2_MAP_CENTRE = 1 };
+// (only when X^2 is bit-for-bit even around N/2; a generator may have shifted X in place, profiles.py:69-70,
+// and then the lens plane is stored unfolded: index pos, P2_MAP_FULL)
+enum { P2_MAP_FREQ = 0, P2_MAP_CENTRE = 1, P2_MAP_FULL = 2 };
 
 template <typename T>
 struct P2Stage {
@@ -62,7 +64,8 @@ struct P2Args {
     P2Stage<T> st[P2_MAX_STAGES];
     cx<T>* ring;              // ring_slots * G planes
     const cx<T>* tw;          // twiddles of LinePlan<N, E>
-    const cx<T>* fac;         // factor plane [N lines][FL], folded (P2_MAP_*)
+    const cx<T>* fac;         // factor plane [N lines][fac_stride], folded or full (P2_MAP_*)
+    int fac_stride;           // samples per factor row
     unsigned int* counters;   // [0] next item; [1 + s*ngroups + g] completed items of (s, g); all zero at launch
     unsigned int* zero_counters;   // the counter set the PREVIOUS launch of the plan used: zeroed by this launch (the plan
     int zero_count;                // alternates between two sets, so no CTA has to find out that it is the last one)
@@ -76,9 +79,11 @@ struct P2Args {
     alignas(64) CUtensorMap tm_out;
 };
 
+// acquire: pairs with the producers' red.release, so that what is read from the ring after the test of the value
+// (by any thread of the CTA, after the CTA barrier that follows) is ordered after the producers' stores
 __device__ __forceinline__ unsigned int p2_ld_relaxed(const unsigned int* ctr) {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr));
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     return v;
 }
 __device__ __forceinline__ void p2_signal(unsigned int* ctr) {
@@ -140,9 +145,9 @@ __device__ __forceinline__ void p2_poll(const P2Args<T>& p, int item, unsigned i
     p2_decode<T, TILES>(p, item, it);
     const unsigned int* done = p.counters + 1;
     const P2Stage<T>& st = p.st[it.s];
-    // relaxed, non-blocking reads: everything that is read once the counters are complete (the ring)
-    // goes to L2 (cp.async.cg), is requested only after a CTA barrier that follows the test of these
-    // values, and was made visible at L2 before the counter was incremented (red.release)
+    // acquire reads: everything that is read once the counters are complete (the ring) is requested only
+    // after a CTA barrier that follows the test of these values, and was made visible before the counter
+    // was incremented (red.release)
     if (it.s > 0) pa = p2_ld_relaxed(&done[(it.s - 1) * p.ngroups + it.g]);
     if (st.out_ring && !st.in_ring && it.g >= p.ring_slots)
         pb = p2_ld_relaxed(&done[(p.nstages - 1) * p.ngroups + (it.g - p.ring_slots)]);
@@ -171,6 +176,7 @@ __device__ __forceinline__ void p2_wait_ready(const P2Args<T>& p, int item, unsi
 template <int N, int E>
 __device__ __forceinline__ int p2_fac_index(int map, int pos, int m) {
     if (map == P2_MAP_FREQ) return (m < E / 2) ? pos : N - pos;
+    if (map == P2_MAP_FULL) return pos;
     return (m < E / 2) ? N / 2 - pos : pos - N / 2;
 }
 
@@ -228,7 +234,7 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
     const long long o_base = (REV ? (long long)(N - t) : (long long)t) * PSTRIDE;
     constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * PSTRIDE;
     const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
-    const cx<T>* fline = p.fac + (long long)fixed * K::FL;      // L2-resident factor row of this line
+    const cx<T>* fline = p.fac + (long long)fixed * p.fac_stride;   // L2-resident factor row of this line
     const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
 
     for (int bi = 0; bi < nb; ++bi) {
@@ -504,12 +510,14 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
 //   kind P2_FAC_H, by_column = 0: line = row j,    fac = H(a[idx], b[j])      (a[i] == a[N - i] bit for bit)
 //   kind P2_FAC_H, by_column = 1: line = column i, fac = H(a[i], b[idx])
 //   kind P2_FAC_LENS:             line = row j,    fac = lens(x2[N/2 - idx], x2[j])   (x2 even around N/2)
+//   kind P2_FAC_LENS, full = 1:   line = row j,    fac = lens(x2[idx], x2[j]), idx = 0 .. N-1 (row stride fl >= N): the
+//                                 grid was shifted in place by a generator and X^2 is not even around N/2
 // FP64 phase with the reference's operation order (kernels.cuh).
 template <typename T>
 __global__ void factor_plane_kernel(cx<T>* __restrict__ fac, const double* __restrict__ a_tab, const double* __restrict__ b_tab,
-                                    const double* __restrict__ x2_tab, int n, int fl, int kind, int by_column, double z,
+                                    const double* __restrict__ x2_tab, int n, int fl, int kind, int by_column, int full, double z,
                                     double lens_k0, double lens_2f) {
-    const int half = n / 2 + 1;
+    const int half = full ? n : n / 2 + 1;
     const long long total = (long long)n * half;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int line = (int)(i / half);
@@ -518,7 +526,7 @@ __global__ void factor_plane_kernel(cx<T>* __restrict__ fac, const double* __res
         if (kind == P2_FAC_H) {
             f = by_column ? transfer_factor<T>(a_tab[line], b_tab[idx], z) : transfer_factor<T>(a_tab[idx], b_tab[line], z);
         } else {
-            f = lens_factor<T>(x2_tab[n / 2 - idx], x2_tab[line], lens_k0, lens_2f);
+            f = lens_factor<T>(x2_tab[full ? idx : n / 2 - idx], x2_tab[line], lens_k0, lens_2f);
         }
         fac[(long long)line * fl + idx] = f;
     }

@@ -26,9 +26,9 @@ struct P2Ops {
 
 const P2Ops<float>* find_p2_f32(int n, int variant);
 const P2Ops<double>* find_p2_f64(int n, int variant);
-cudaError_t p2_factor_plane_f32(float2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+cudaError_t p2_factor_plane_f32(float2* fac, const double* tabs, int n, int fl, int kind, int by_column, int full, double z,
                                 double k0, double two_f, cudaStream_t s);
-cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl, int kind, int by_column, double z,
+cudaError_t p2_factor_plane_f64(double2* fac, const double* tabs, int n, int fl, int kind, int by_column, int full, double z,
                                 double k0, double two_f, cudaStream_t s);
 
 extern long long g_launches;

@@ -157,10 +157,12 @@ class EnsemblePropagator:
                        "propagate_field")
         return out
 
-    def intensity_from_host(self, host_fields, z, chunk=16, out=None):
+    def intensity_from_host(self, host_fields, z, chunk=16, out=None, sync=True):
         """End-to-end form: ``host_fields`` is a pinned (or pageable) CPU tensor / numpy array of
         shape (B, N, N); every chunk is copied H2D, propagated and its intensity copied D2H, with the
-        copies of neighbouring chunks overlapped on three streams.  Returns a pinned CPU tensor."""
+        copies of neighbouring chunks overlapped on three streams.  Returns a pinned CPU tensor that is
+        complete when the call returns (``sync=False``: the caller synchronises the current stream before
+        reading it, e.g. to queue several ensembles back to back)."""
         torch = _torch()
         if isinstance(host_fields, np.ndarray):
             host_fields = torch.from_numpy(host_fields)
@@ -192,6 +194,10 @@ class EnsemblePropagator:
                 out[b0:b0 + nb].copy_(dev_out[k % nbuf][:nb], non_blocking=True)
         for s in streams:
             cur.wait_stream(s)
+        if sync:
+            # the D2H copies are asynchronous (pinned destination): the host may read `out` only once they landed
+            for s in streams:
+                s.synchronize()
         return out
 
 

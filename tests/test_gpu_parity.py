@@ -182,6 +182,51 @@ def test_golden_update_obj():
     assert repr(b) == str(g["repr"])
 
 
+@pytest.mark.parametrize("bits", BITS)
+def test_golden_lens_on_shifted_grid(bits):
+    """Reference output for lens() after gaussian_beam(x0, y0 != 0) shifted X in place, at a size the fused
+    step kernel serves (its lens factor plane must not be folded about the grid centre then)."""
+    g = golden(f"lens_shifted_c{bits}")
+    b = Beam2D(3 * mm, 256, 632 * nm, init_field_gen=lp.gaussian_beam,
+               init_gen_args=(1., 0.03, 0.011, -0.007), complex_bits=bits)
+    assert np.array_equal(b.X, g["X"])
+    b.lens(2.)
+    assert rel_l2(b.field, g["field_lens"]) <= TOL[bits]
+    b.propagate(0.7)
+    assert rel_l2(b.field, g["field"]) <= TOL[bits]
+
+
+@pytest.mark.parametrize("bits,n", [(64, 128), (64, 256), (64, 512), (64, 1024), (64, 2048),
+                                    (128, 128), (128, 256), (128, 512), (128, 1024)])
+def test_shifted_grid_lens_vs_oracle(bits, n):
+    """profiles.py:69-70 + beam2d.py:508-511 at every size class of lens(): fused step kernel (256-1024
+    complex64, 256-512 complex128) and one kernel per pass; single beam and a batch (3 beams share the grid)."""
+    args = (1., 0.03, 0.011, -0.007)
+
+    def gen3(X, Y, *a):                       # ONE in-place shift, three beams on the shifted grid
+        f = lp.gaussian_beam(X, Y, *a)
+        return np.stack([f, 0.5j * f, (1 - 2j) * f[::-1].copy()])
+
+    for gen in (lp.gaussian_beam, gen3):
+        b = Beam2D(3 * mm, n, 632 * nm, init_field_gen=gen, init_gen_args=args, complex_bits=bits)
+        o = orc.OracleBeam(3 * mm, n, 632 * nm, init_field_gen=gen, init_gen_args=args, complex_bits=bits)
+        assert np.array_equal(b.X, o.X) and np.array_equal(b.Y, o.Y)
+        x2 = b.X ** 2
+        assert not np.array_equal(x2[1:n // 2][::-1], x2[n // 2 + 1:])
+        for f, z in ((2., 0.7), (-0.4, 0.05)):
+            b.lens(f); o.lens(f)
+            assert rel_l2(b.field, o.field) <= TOL[bits], (f, "lens field")
+            assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits], (f, "lens spectrum")
+            b.propagate(z); o.propagate(z)
+            assert rel_l2(b.field, o.field) <= TOL[bits], (f, z)
+            assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits], (f, z)
+    # an unshifted beam on the same (n, area, wl) afterwards gets its own plan (x2 is part of the key)
+    c = Beam2D(3 * mm, n, 632 * nm, init_field_gen=lp.gaussian_beam, init_gen_args=(1., 0.03), complex_bits=bits)
+    oc = orc.OracleBeam(3 * mm, n, 632 * nm, init_field_gen=lp.gaussian_beam, init_gen_args=(1., 0.03), complex_bits=bits)
+    c.lens(2.); oc.lens(2.)
+    assert rel_l2(c.spectrum, oc.spectrum) <= TOL[bits]
+
+
 # --------------------------------------------------------------- oracle, seeded inputs
 @pytest.mark.parametrize("bits", BITS)
 @pytest.mark.parametrize("seed", range(8))
@@ -218,6 +263,27 @@ def test_oracle_chain_sizes(bits, n):
         assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits], (f, z)
     b.propagate(0); o.propagate(0)
     assert b.z == o.z
+
+
+@pytest.mark.parametrize("bits,n", [(64, 4096), (128, 4096), (64, 8192)])
+def test_oracle_large_sizes(bits, n):
+    """configs[1]'s largest sizes (tests/gaussbeam_performance.py:16-30: rectangle_hole, area 0.4 cm, wl 532 nm)
+    against the numpy oracle itself, not only through properties: fft2, lens + fft2, propagate, iprofile."""
+    area, wl = 4e-1, 532e-7
+    rng = np.random.default_rng(77 + n)
+    x = np.arange(-n // 2, n // 2) * (area / n)
+    hole = lp.rectangle_hole(x, x.reshape(-1, 1), 2e-1, 1e-1)
+    f0 = (hole * rng.uniform(0.5, 1.0, size=(n, n)) * np.exp(2j * np.pi * rng.uniform(size=(n, n)))).astype(CT[bits])
+    del hole
+    b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    o = orc.OracleBeam(area, n, wl, init_field=f0, complex_bits=bits)
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    b.lens(0.3); o.lens(0.3)
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    b.propagate(0.7); o.propagate(0.7)
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits]
 
 
 @pytest.mark.parametrize("bits", BITS)
