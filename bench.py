@@ -14,7 +14,9 @@ scaling), beams sharded across ranks with no collective on the data path.
              copies the intensities D2H, copies inside the timed region
   roofline   dominant kernel timed alone with CUDA events on the launching stream
   cpu_baseline / --impl reference
-             the numpy oracle port of the reference path on the box's host cores
+             the reference's OWN lightprop2d.Beam2D (numpy path; installed unmodified under oracle/_ref by
+             oracle/build_ref.py and imported through the cupy stub of oracle/ref_shim.py) on the box's host
+             cores, one process per core; the oracle port only if oracle/_ref did not travel
 """
 import argparse
 import json
@@ -102,32 +104,103 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------- CPU reference arm
-def _cpu_worker(args):
-    """One oracle process: `steps` stateful propagate steps on its own 1024^2 complex64 beam."""
-    seed, steps, n, bits = args
-    import numpy as np
+def _ref_kind():
+    """'reference' when the unmodified reference package can be imported here, else 'port' (the oracle)."""
+    try:
+        from oracle import ref_shim
+        return "reference" if ref_shim.available() else "port"
+    except Exception:
+        return "port"
+
+
+def _make_beam(kind, field, bits):
+    if kind == "reference":
+        from oracle import ref_shim
+        ref = ref_shim.load()
+        return ref.Beam2D(AREA, field.shape[-1], WL, init_field=field, complex_bits=bits)
     from oracle import beam_oracle as orc
+    return orc.OracleBeam(AREA, field.shape[-1], WL, init_field=field, complex_bits=bits)
+
+
+def _cpu_worker(args):
+    """One host process.  mode 'state': `warm` + `steps` stateful propagate(DZ) steps on its own beam (the metric);
+    mode 'e2e': per step a NEW field is seeded (`_update_obj`: fft2), propagated and its iprofile read -- the work
+    the GPU arm's e2e does per beam (fft2 -> H -> ifft2 -> |E|^2)."""
+    seed, warm, steps, n, bits, kind, mode = args
+    import numpy as np
     rng = np.random.default_rng(seed)
     ct = np.complex64 if bits == 64 else np.complex128
     f = (rng.uniform(size=(n, n)) * np.exp(2j * np.pi * rng.uniform(size=(n, n)))).astype(ct)
-    b = orc.OracleBeam(AREA, n, WL, init_field=f, complex_bits=bits)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        b.propagate(DZ)
+    b = _make_beam(kind, f.copy(), bits)
+    acc = 0.0
+    for i in range(warm + steps):
+        if i == warm:
+            t0 = time.perf_counter()
+        if mode == "state":
+            b.propagate(DZ)
+        else:
+            if kind == "reference":
+                b._update_obj(f.copy())
+            else:
+                b.update(f.copy())
+            b.propagate(DZ)
+            acc += float(b.iprofile[0, 0])
     return time.perf_counter() - t0
 
 
-def cpu_arm(steps, warmup, procs):
-    """numpy oracle port of the reference path, one process per host core; every step = one
-    propagate on `procs` independent beams (a bounded sample of the GPU workload)."""
+def cpu_arm(steps, warmup, procs, kind, mode="state", n=None, bits=None):
+    """One process per host core (numpy's pocketfft is single-threaded); every step = one propagate on `procs`
+    independent beams, a bounded sample of the GPU workload.  Returns (beam-propagations / s, seconds)."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
+    n = N_GRID if n is None else n
+    bits = BITS if bits is None else bits
     with ctx.Pool(procs) as pool:
-        pool.map(_cpu_worker, [(i, max(1, warmup), N_GRID, BITS) for i in range(procs)])
-        # every worker times its own `steps` propagate calls (construction excluded); the
+        # every worker times its own `steps` calls after `warmup` untimed ones (construction excluded); the
         # processes run concurrently, the slowest one bounds the job
-        dt = max(pool.map(_cpu_worker, [(i, steps, N_GRID, BITS) for i in range(procs)]))
+        dt = max(pool.map(_cpu_worker, [(i, warmup, steps, n, bits, kind, mode) for i in range(procs)]))
     return procs * steps / dt, dt
+
+
+def secondary_baselines():
+    """north_star's secondary references: the reference's pyfftw CPU path and its cupy / cuFFT GPU path.  Neither
+    package is in this image (no network): reported as unavailable rather than substituted."""
+    out = {}
+    for mod, what in (("pyfftw", "reference CPU path with pyfftw (beam2d.py:25-34)"),
+                      ("cupy", "reference GPU path, cupy + cuFFT (beam2d.py:17-23, 106-109)")):
+        try:
+            __import__(mod)
+            out[mod] = {"available": True, "what": what}
+        except Exception as e:                                   # noqa: BLE001
+            out[mod] = {"available": False, "what": what, "unavailable": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def time_secondary(sec, procs):
+    """Time whichever secondary reference paths are importable (bounded); fills `value` in place."""
+    if sec.get("pyfftw", {}).get("available") and _ref_kind() == "reference":
+        # with pyfftw importable the reference selects it by itself (beam2d.py:25-34), threads = -1: one process
+        v, dt = cpu_arm(steps=10, warmup=2, procs=1, kind="reference")
+        sec["pyfftw"].update({"value": v, "unit": UNIT, "sample": f"1 process x 10 propagate steps ({dt:.1f} s), FFTW threads=-1"})
+    if sec.get("cupy", {}).get("available") and _ref_kind() == "reference":
+        try:
+            import cupy as cp
+            import numpy as np
+            from oracle import ref_shim
+            ref = ref_shim.load()
+            f = cp.asarray(np.random.default_rng(0).uniform(size=(N_GRID, N_GRID)).astype(np.complex64))
+            b = ref.Beam2D(AREA, N_GRID, WL, init_field=f, complex_bits=BITS, use_gpu=True)
+            for _ in range(3):
+                b.propagate(DZ)
+            cp.cuda.Stream.null.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                b.propagate(DZ)
+            cp.cuda.Stream.null.synchronize()
+            sec["cupy"].update({"value": 20 / (time.perf_counter() - t0), "unit": UNIT, "sample": "1 beam x 20 propagate steps"})
+        except Exception as e:                                   # noqa: BLE001
+            sec["cupy"].update({"available": False, "unavailable": f"{type(e).__name__}: {e}"})
+    return sec
 
 
 def run_reference(args):
@@ -136,25 +209,87 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    steps, warmup = max(1, args.steps), max(1, args.warmup)
-    # keep the run bounded: ~0.07 s per 1024^2 complex64 step per core
-    steps = min(steps, 40)
-    warmup = min(warmup, 3)
-    value, dt = cpu_arm(steps, warmup, procs)
-    sample = (f"{procs} processes x {steps} propagate steps, one {N_GRID}^2 complex64 beam each "
+    kind = _ref_kind()
+    # the driver's K and W are honoured; one step costs ~0.07 s per core, so even K = 1000 stays within minutes
+    steps, warmup = max(1, min(args.steps, 1000)), max(0, min(args.warmup, 100))
+    value, dt = cpu_arm(steps, warmup, procs, kind)
+    e2e_steps = max(3, min(steps, 10))
+    e2e_value, e2e_dt = cpu_arm(e2e_steps, 1, procs, kind, mode="e2e")
+    who = ("lightprop2d.Beam2D of the unmodified reference (oracle/_ref), numpy path" if kind == "reference"
+           else "numpy oracle port of lightprop2d.Beam2D (oracle/_ref absent)")
+    sample = (f"{procs} processes x {steps} propagate steps (+{warmup} warm-up), one {N_GRID}^2 complex64 beam each "
               f"(numpy pocketfft is single-threaded: one process per host core)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 transforms, f64 phase", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "impl_note": "numpy oracle port of lightprop2d.Beam2D.propagate on host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "impl_note": who + " on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+        # same work per beam as the GPU arm's e2e (a new host field each step: fft2 -> H -> ifft2 -> |E|^2);
+        # host only, so no bytes cross a link
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "steps": e2e_steps, "work": "per beam: _update_obj(field) [fft2] -> propagate(dz) -> iprofile",
+                "stateful_value": value},
+        "secondary_baselines": time_secondary(secondary_baselines(), procs),
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------ our arm
+def ctypes_name(lib, plan):
+    import ctypes as C
+    buf = C.create_string_buffer(240)
+    lib.lp2d_plan_step_kernel(plan, buf, 240)
+    return buf.value.decode()
+
+
+def slab_record(rank, world, dev, dist):
+    """BASELINE config 4 on the ranks of this run: ONE complex64 grid (32768^2 = 8 GiB on 8 GPUs, 16384^2 on 2 / 4)
+    decomposed in row slabs, propagate = local H + column pass, NCCL all-to-all transpose over NVLink, local row
+    pass.  Parity at full size against the plane-wave closed form (tools/planewave_check.py); CUDA events, max
+    over ranks."""
+    import torch
+    from lightprop2d_b200.slab import SlabBeam2D, slab_rows
+    from tools import planewave_check as pw
+    n = 32768 if world >= 8 else 16384
+    rec = {"npoints": n, "complex_bits": 64, "ranks": world}
+    try:
+        rec["planewave_rel_l2"] = pw.check(n, 64, AREA * n / 1024, WL, DZ, rank, world)
+        rec["parity_ok"] = max(rec["planewave_rel_l2"].values()) <= 1e-5
+        torch.cuda.empty_cache()
+        r0, r1 = slab_rows(n, rank, world)
+        g = torch.Generator(device=dev)
+        g.manual_seed(7 + rank)
+        f = torch.polar(torch.rand(r1 - r0, n, generator=g, device=dev),
+                        torch.rand(r1 - r0, n, generator=g, device=dev) * 6.2831853).to(torch.complex64)
+        b = SlabBeam2D(AREA * n / 1024, n, WL, init_field=f, complex_bits=64)
+        del f
+        for _ in range(3):
+            b.propagate(DZ)
+        torch.cuda.synchronize()
+        dist.barrier()
+        Ks = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Ks):
+            b.propagate(DZ)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / Ks], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        sent = n * n * 8 * (world - 1) // (world * world)
+        rec.update({"ms_per_propagate": ms, "propagations_per_s": 1e3 / ms,
+                    "nvlink_bytes_sent_per_rank": sent, "nvlink_gbs_per_rank": sent / (ms * 1e-3) / 1e9,
+                    "wire_time_ms_at_770gbs": sent / 770e9 * 1e3,
+                    "hbm_alg_gbs_per_gpu": 3 * n * n * 8 / world / (ms * 1e-3) / 1e9})
+        del b
+        torch.cuda.empty_cache()
+    except Exception as e:                                    # noqa: BLE001  (reported, never hidden)
+        rec["error"] = f"{type(e).__name__}: {e}"
+    return rec
+
+
 def run_ours(args):
     import ctypes as C
     import numpy as np
@@ -310,29 +445,106 @@ def run_ours(args):
     a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(Ke):
-        prop.intensity_from_host(host_in, DZ, chunk=8, out=host_out)
+        prop.intensity_from_host(host_in, DZ, chunk=8, out=host_out)      # returns with the result on the host
     b_.record()
     torch.cuda.synchronize()
     e2e_ms = max(a.elapsed_time(b_), (time.perf_counter() - t0) * 1e3)
     barrier()
+    # host-link roofline of that step: the same bytes (H2D of the fields, D2H of the intensities) as plain
+    # concurrent copies on two streams, all ranks at the same time, no kernel
+    dev_in = torch.empty(E2E_BEAMS, n, n, dtype=torch.complex64, device=dev)
+    dev_out = torch.empty(E2E_BEAMS, n, n, dtype=torch.float32, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def link_pass():
+        with torch.cuda.stream(s_in):
+            dev_in.copy_(host_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host_out.copy_(dev_out, non_blocking=True)
+    for _ in range(2):
+        link_pass()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        link_pass()
+    torch.cuda.synchronize()
+    link_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    del dev_in, dev_out
     if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([e2e_ms, link_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e = {"value": E2E_BEAMS * world * Ke / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": E2E_BEAMS * n * n * 8, "d2h_bytes_per_step": E2E_BEAMS * n * n * 4,
+        e2e_ms, link_ms = float(t[0].item()), float(t[1].item())
+    h2d_b, d2h_b = E2E_BEAMS * n * n * 8, E2E_BEAMS * n * n * 4
+    e2e_value = E2E_BEAMS * world * Ke / (e2e_ms * 1e-3)
+    link_value = E2E_BEAMS * world * Ke / (link_ms * 1e-3)
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
            "steps": Ke, "beams_per_step_per_gpu": E2E_BEAMS,
-           "api": "EnsemblePropagator.intensity_from_host (fft2 -> H -> ifft2 -> |E|^2 per beam)"}
+           "api": "EnsemblePropagator.intensity_from_host (fft2 -> H -> ifft2 -> |E|^2 per beam; result on the host at return)",
+           "host_link_roofline": {
+               "value": link_value, "unit": UNIT, "frac": e2e_value / link_value,
+               "h2d_gbs": h2d_b * world * Ke / (link_ms * 1e-3) / 1e9, "d2h_gbs": d2h_b * world * Ke / (link_ms * 1e-3) / 1e9,
+               "how": "the step's H2D + D2H bytes as bare concurrent cudaMemcpyAsync on two streams from the same pinned "
+                      "buffers, all ranks at once, max over ranks (aggregate GB/s over the N GPUs)"}}
+
+    # ---- complex128 (BASELINE metric: c64 / c128): the same stateful step on 1024^2 complex128 beams
+    c128 = None
+    try:
+        B128 = 128                                            # 2 GiB spectrum + 2 GiB field
+        g.manual_seed(4321 + lo)
+        f128 = torch.polar(torch.rand(B128, n, n, generator=g, device=dev, dtype=torch.float64),
+                           torch.rand(B128, n, n, generator=g, device=dev, dtype=torch.float64) * (2 * np.pi))
+        beam128 = lp.Beam2D(AREA, n, WL, init_field=f128, complex_bits=128, use_gpu=True, numpy_output=False, device=local_rank)
+        del f128
+        beam128.spectrum
+        for _ in range(3):
+            beam128.propagate(DZ)
+        torch.cuda.synchronize()
+        barrier()
+        K128 = max(3, min(K, 20))
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K128):
+            beam128.propagate(DZ)
+        b_.record()
+        torch.cuda.synchronize()
+        ms128 = a.elapsed_time(b_)
+        if world > 1:
+            t = torch.tensor([ms128], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms128 = float(t.item())
+        nb = ctypes_name(lib, beam128._plan.handle)
+        alg128 = 3 * n * n * 16 * B128
+        c128 = {"value": B128 * world * K128 / (ms128 * 1e-3), "unit": UNIT, "ms_per_step": ms128 / K128, "steps": K128,
+                "workload": f"batched {n}x{n} complex128 stateful Beam2D.propagate(dz), {B128} beams per GPU",
+                "kernel": nb, "roofline_frac": alg128 / (ms128 / K128 * 1e-3) / 1e9 / peak,
+                "algorithmic_bytes_per_step": alg128}
+        del beam128
+        torch.cuda.empty_cache()
+    except Exception as e:                                    # noqa: BLE001  (reported, never hidden)
+        c128 = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- one grid over all the ranks (BASELINE config 4): slab decomposition + all-to-all exchange, N >= 2
+    slab = None
+    if world > 1:
+        slab = slab_record(rank, world, dev, dist)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload on host cores
     cpu = None
+    sec = secondary_baselines()
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         procs = max(1, min(cores, 64))
-        cpu_steps = 40          # ~2 s of wall clock, ~30 core-seconds of CPU work on a 16-core box
-        cv, cdt = cpu_arm(steps=cpu_steps, warmup=2, procs=procs)
-        cpu = {"value": cv, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": f"{procs} oracle processes x {cpu_steps} propagate steps on one {n}^2 complex64 beam each ({cdt:.1f} s)"}
+        kind = _ref_kind()
+        cpu_steps = 40          # ~3 s of wall clock, ~45 core-seconds of CPU work on a 16-core box
+        cv, cdt = cpu_arm(steps=cpu_steps, warmup=2, procs=procs, kind=kind)
+        cpu = {"value": cv, "unit": UNIT, "cores": procs, "kind": kind,
+               "sample": f"{procs} processes x {cpu_steps} propagate steps of "
+                         f"{'the reference lightprop2d.Beam2D (oracle/_ref)' if kind == 'reference' else 'the oracle port'} "
+                         f"on one {n}^2 complex64 beam each ({cdt:.1f} s)"}
+        sec = time_secondary(sec, procs)
 
     if rank == 0:
         line = {
@@ -343,7 +555,10 @@ def run_ours(args):
                        "total_beams": total_beams, "sharding": "contiguous beam blocks, no collective",
                        "l2": "inputs (2 GiB spectrum + 2 GiB field per GPU) are larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "c128": c128, "secondary_baselines": sec,
         }
+        if slab is not None:
+            line["slab"] = slab
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -120,10 +120,18 @@ __host__ __device__ constexpr int bitrev(int k, int bits) {
 // R-point forward DFT on registers, natural order in and out (R = 2..32, power of two).
 // Radix-2 decimation in frequency; the twiddles and the final bit reversal are
 // compile-time after unrolling (register renaming only).
-template <typename T, int R>
-__device__ __forceinline__ void dft_reg(cx<T> (&x)[R]) {
+// Hooks: `pre(i, x[i])` is called when input i is first touched (its value is still the input), `post(k, y[k])`
+// when output k (natural order) has its final value.  They let the caller spread the global stores of the state
+// before the transform / of the result after it between the butterflies instead of issuing 32 of them in a row
+// (a store burst fills the load/store queue and stalls the warp; profiles/r2e_*).
+struct NoHook {
+    template <typename C> __device__ __forceinline__ void operator()(int, const C&) const {}
+};
+
+template <typename T, int R, typename PRE = NoHook, typename POST = NoHook>
+__device__ __forceinline__ void dft_reg(cx<T> (&x)[R], PRE pre = PRE(), POST post = POST()) {
     static_assert(R >= 1 && R <= 32 && (R & (R - 1)) == 0, "radix");
-    if (R == 1) return;
+    if (R == 1) { pre(0, x[0]); post(0, x[0]); return; }
 #pragma unroll
     for (int s = R / 2; s >= 1; s >>= 1) {
 #pragma unroll
@@ -132,8 +140,10 @@ __device__ __forceinline__ void dft_reg(cx<T> (&x)[R]) {
             const int i0 = (k / s) * 2 * s + pos;
             const int i1 = i0 + s;
             const cx<T> a = x[i0], b = x[i1];
+            if (s == R / 2) { pre(i0, a); pre(i1, b); }
             x[i0] = cadd(a, b);
             x[i1] = mul_w32<T>(csub(a, b), pos * (16 / s));
+            if (s == 1) { post(bitrev(i0, ilog2(R)), x[i0]); post(bitrev(i1, ilog2(R)), x[i1]); }
         }
     }
     cx<T> y[R];
@@ -178,7 +188,9 @@ struct LinePlan {
 };
 
 // How the TPL threads of one line synchronise around a shared-memory exchange.
-enum { SYNC_WARP = 0, SYNC_NAMED = 1, SYNC_CTA = 2 };
+// SYNC_CONSUMERS: the transform threads of a warp-specialised CTA (pipe3.cuh) without its helper warps
+enum { SYNC_WARP = 0, SYNC_NAMED = 1, SYNC_CTA = 2, SYNC_CONSUMERS = 3 };
+#define LP2D_Q4_CONSUMER_THREADS 256
 
 template <int MODE, int TPL>
 __device__ __forceinline__ void line_sync(int line_in_cta) {
@@ -186,15 +198,26 @@ __device__ __forceinline__ void line_sync(int line_in_cta) {
         __syncwarp();
     } else if (MODE == SYNC_NAMED) {
         asm volatile("bar.sync %0, %1;" ::"r"(line_in_cta + 1), "r"(TPL) : "memory");
+    } else if (MODE == SYNC_CONSUMERS) {
+        asm volatile("bar.sync 15, %0;" ::"n"(LP2D_Q4_CONSUMER_THREADS) : "memory");
     } else {
         __syncthreads();
     }
 }
 
 // One pass of the schedule on the thread's registers v[E].
-template <typename T, int N, int E, int P, int SYNC>
+// TWS: the twiddle table is in shared memory (plain loads) instead of global memory (read-only path)
+template <bool TWS, typename C>
+__device__ __forceinline__ C tw_load(const C* p) {
+    if constexpr (TWS) return *p;
+    else return __ldg(p);
+}
+
+// pre(m, v[m]) in the first pass / post(m, v[m]) in the last pass: see dft_reg (m = register slot, line position
+// t + TPL*m)
+template <typename T, int N, int E, int P, int SYNC, bool TWS = false, typename PRE = NoHook, typename POST = NoHook>
 __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sline,
-                                          const cx<T>* __restrict__ tw, int t, int line_in_cta) {
+                                          const cx<T>* __restrict__ tw, int t, int line_in_cta, PRE pre = PRE(), POST post = POST()) {
     using LP = LinePlan<N, E>;
     constexpr int R = LP::radix(P);
     constexpr int Ns = LP::ns(P);
@@ -227,9 +250,9 @@ __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sli
                 // the FP pipe, is the scarce resource of the fused kernel
                 cx<T> wb[3], wa[7];
 #pragma unroll
-                for (int b = 1; b < 4; ++b) wb[b - 1] = __ldg(&tw[twoff + (b - 1) * Ns + k]);
+                for (int b = 1; b < 4; ++b) wb[b - 1] = tw_load<TWS>(&tw[twoff + (b - 1) * Ns + k]);
 #pragma unroll
-                for (int a = 1; a < 8; ++a) wa[a - 1] = __ldg(&tw[twoff + (4 * a - 1) * Ns + k]);
+                for (int a = 1; a < 8; ++a) wa[a - 1] = tw_load<TWS>(&tw[twoff + (4 * a - 1) * Ns + k]);
 #pragma unroll
                 for (int r = 1; r < R; ++r) {
                     if ((r >> 2) > 0) u[r] = cmul(u[r], wa[(r >> 2) - 1]);
@@ -242,17 +265,25 @@ __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sli
                 for (int r0 = 1; r0 < R; r0 += 8) {
                     cx<T> w[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) if (r0 + i < R) w[i] = __ldg(&tw[twoff + (r0 + i - 1) * Ns + k]);
+                    for (int i = 0; i < 8; ++i) if (r0 + i < R) w[i] = tw_load<TWS>(&tw[twoff + (r0 + i - 1) * Ns + k]);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) if (r0 + i < R) u[r0 + i] = cmul(u[r0 + i], w[i]);
                     asm volatile("" ::: "memory");
                 }
             } else {
 #pragma unroll
-                for (int r = 1; r < R; ++r) u[r] = cmul(u[r], __ldg(&tw[twoff + (r - 1) * Ns + k]));
+                for (int r = 1; r < R; ++r) u[r] = cmul(u[r], tw_load<TWS>(&tw[twoff + (r - 1) * Ns + k]));
             }
         }
-        dft_reg<T, R>(u);
+        if constexpr (P == 0 && last) {
+            dft_reg<T, R>(u, [&](int r, const cx<T>& val) { pre(q + r * Q, val); }, [&](int r, const cx<T>& val) { post(q + r * Q, val); });
+        } else if constexpr (P == 0) {
+            dft_reg<T, R>(u, [&](int r, const cx<T>& val) { pre(q + r * Q, val); }, NoHook());
+        } else if constexpr (last) {
+            dft_reg<T, R>(u, NoHook(), [&](int r, const cx<T>& val) { post(q + r * Q, val); });
+        } else {
+            dft_reg<T, R>(u);
+        }
         if (last) {
 #pragma unroll
             for (int r = 0; r < R; ++r) v[q + r * Q] = u[r];
@@ -278,10 +309,12 @@ __device__ __forceinline__ void line_pass(cx<T> (&v)[E], cx<T>* __restrict__ sli
 // Exchange-buffer contract: every scatter is preceded by a sync of the line's
 // threads, so back-to-back calls on the same sline (next line of a loop, or the
 // inverse transform that follows the transfer function) need no extra barrier.
-template <typename T, int N, int E, int SYNC, int P = 0>
-__device__ __forceinline__ void line_fft(cx<T> (&v)[E], cx<T>* sline, const cx<T>* tw, int t, int line_in_cta) {
-    line_pass<T, N, E, P, SYNC>(v, sline, tw, t, line_in_cta);
-    if constexpr (P + 1 < LinePlan<N, E>::npass()) line_fft<T, N, E, SYNC, P + 1>(v, sline, tw, t, line_in_cta);
+template <typename T, int N, int E, int SYNC, int P = 0, bool TWS = false, typename PRE = NoHook, typename POST = NoHook>
+__device__ __forceinline__ void line_fft(cx<T> (&v)[E], cx<T>* sline, const cx<T>* tw, int t, int line_in_cta, PRE pre = PRE(),
+                                         POST post = POST()) {
+    line_pass<T, N, E, P, SYNC, TWS, PRE, POST>(v, sline, tw, t, line_in_cta, pre, post);
+    if constexpr (P + 1 < LinePlan<N, E>::npass())
+        line_fft<T, N, E, SYNC, P + 1, TWS, PRE, POST>(v, sline, tw, t, line_in_cta, pre, post);
 }
 
 }  // namespace lp2d

@@ -11,6 +11,7 @@
 #include "pipe2_ops.cuh"
 #include "xl_line.cuh"
 
+
 namespace lp2d {
 long long g_launches = 0;
 
@@ -103,6 +104,12 @@ struct lp2d_plan {
     // fused step kernel (pipe2.cuh)
     const P2Ops<float>* p2_32;
     const P2Ops<double>* p2_64;
+    // persistent form of the fused step kernel (pipe3.cuh); used instead of the ticket form when present and enabled
+    const Q4Ops<float>* q4_32;
+    const Q4Ops<double>* q4_64;
+    int q4_ctas;               // resident CTAs per SM (1)
+    int q4_lag;                // tuning override (0 = automatic)
+    int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
     int p2_ctas_factor, p2_ctas_plain;
     void* p2_tw;               // twiddles of the P2 (N, E) schedule
     void* p2_fac;              // factor plane [n][fl]
@@ -242,6 +249,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         if (host_a[k] != host_a[n - k] || host_b[k] != host_b[n - k]) p->h_even = false;
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
+    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -282,6 +290,30 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
                 return e != cudaSuccess ? cuda_fail(e, "fused step kernel setup") : fail(LP2D_ECUDA, "fused step kernel does not fit an SM");
             }
             p->p2_32 = q32; p->p2_64 = q64; p->ring_bytes = ring_bytes;
+            // The persistent warp-specialised form (pipe3.cuh) exists where an instance with the same (N, E) schedule
+            // does (it shares the twiddle table and the factor plane).  LP2D_Q4_OPS: which steps use it (bit 0 plain
+            // fft2, bit 1 steps that store state, bit 2 the fresh chain); default = where it measured faster than the
+            // ticket form (profiles/r2g_sweep1024.log: plain fft2 at 1024 points 4.92 vs 5.57 us per beam; the steps
+            // with a state store 6.9 vs 6.6).  LP2D_PIPE_FORM=4 / 3 forces it everywhere / nowhere.
+            {
+                env = getenv("LP2D_Q4_VARIANT");
+                const int qvar = env ? atoi(env) : 0;
+                const Q4Ops<float>* r32 = dtype == LP2D_C64 ? find_q4_f32(n, qvar) : nullptr;
+                const Q4Ops<double>* r64 = dtype == LP2D_C128 ? find_q4_f64(n, qvar) : nullptr;
+                const int e_p2 = q32 ? q32->e : q64->e;
+                if ((r32 && r32->e == e_p2) || (r64 && r64->e == e_p2)) {
+                    int ctas = 0;
+                    e = r32 ? r32->configure(&ctas) : r64->configure(&ctas);
+                    if (e == cudaSuccess && ctas >= 1) { p->q4_32 = r32; p->q4_64 = r64; p->q4_ctas = ctas; }
+                    else cudaGetLastError();
+                }
+                int q4_default = (dtype == LP2D_C64 && n == 1024) ? 1 : 0;
+                env = getenv("LP2D_PIPE_FORM");
+                if (env != nullptr) q4_default = atoi(env) == 4 ? 7 : 0;
+                env = getenv("LP2D_Q4_OPS");
+                p->q4_ops = env ? atoi(env) : q4_default;
+            }
+            env = getenv("LP2D_Q4_LAG"); p->q4_lag = env ? atoi(env) : 0;
         }
     }
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
@@ -328,9 +360,12 @@ int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
     const bool fused = (p->p2_32 != nullptr || p->p2_64 != nullptr) && (p->fused_ops & 2);
     if (name != nullptr && name_len > 0) {
         if (fused) {
-            const int e = p->p2_32 ? p->p2_32->e : p->p2_64->e, w = p->p2_32 ? p->p2_32->w : p->p2_64->w;
-            snprintf(name, (size_t)name_len, "%s<%s, N=%d, E=%d, W=%d> fused step (rows -> L2 ring -> columns, one launch)",
-                     "t3_kernel", p->dtype == LP2D_C64 ? "float" : "double", p->n, e, w);
+            const bool q4 = (p->q4_32 != nullptr || p->q4_64 != nullptr) && (p->q4_ops & 2);
+            const int e = p->p2_32 ? p->p2_32->e : p->p2_64->e;
+            const int w = q4 ? (p->q4_32 ? p->q4_32->w : p->q4_64->w) : (p->p2_32 ? p->p2_32->w : p->p2_64->w);
+            snprintf(name, (size_t)name_len, "%s<%s, N=%d, E=%d, W=%d> fused step (rows -> L2 ring -> columns, one launch%s)",
+                     q4 ? "q4_kernel" : "t3_kernel", p->dtype == LP2D_C64 ? "float" : "double", p->n, e, w,
+                     q4 ? ", persistent: TMA / bulk-copy producer + transform warps" : "");
         } else {
             const int e = p->ops32 ? p->ops32->e : p->ops64->e;
             snprintf(name, (size_t)name_len, "line_kernel<%s, N=%d, E=%d> row pass + column pass", p->dtype == LP2D_C64 ? "float" : "double", p->n, e);
@@ -375,6 +410,10 @@ template <typename T> const XlOps<T>* xl_of(const lp2d_plan* p);
 template <> const XlOps<float>* xl_of<float>(const lp2d_plan* p) { return p->xl32; }
 template <> const XlOps<double>* xl_of<double>(const lp2d_plan* p) { return p->xl64; }
 
+template <typename T> const Q4Ops<T>* q4_of(const lp2d_plan* p);
+template <> const Q4Ops<float>* q4_of<float>(const lp2d_plan* p) { return p->q4_32; }
+template <> const Q4Ops<double>* q4_of<double>(const lp2d_plan* p) { return p->q4_64; }
+
 template <typename T> const P2Ops<T>* p2_of(const lp2d_plan* p);
 template <> const P2Ops<float>* p2_of<float>(const lp2d_plan* p) { return p->p2_32; }
 template <> const P2Ops<double>* p2_of<double>(const lp2d_plan* p) { return p->p2_64; }
@@ -402,12 +441,103 @@ int p2_ensure_factor(lp2d_plan* p, int kind, int by_column, double p0, double p1
 // Run a chain of `nstages` line passes over `batch` beams in one launch of the fused step kernel.
 // fac_kind: P2_FAC_NONE / P2_FAC_H (p0 = z) / P2_FAC_LENS (p0 = k0, p1 = 2f); by_column: layout of the
 // factor plane (1 for the fused column stage).  Returns -1 when the kernel is not available.
+// stream hand-over of the plan's fused-step state (ring, counters, factor plane)
+static int p2_claim_stream(lp2d_plan* p, cudaStream_t s) {
+    if (p->p2_used && p->p2_stream != s) {
+        if (cudaEventRecord(p->p2_done, p->p2_stream) == cudaSuccess) {
+            LP2D_CU(cudaStreamWaitEvent(s, p->p2_done, 0), "fused step: wait for the previous stream");
+        } else {
+            cudaGetLastError();                     // the previous stream no longer exists: wait for the device
+            LP2D_CU(cudaDeviceSynchronize(), "fused step: device synchronise");
+        }
+    }
+    p->p2_stream = s; p->p2_used = true;
+    return LP2D_OK;
+}
+
+// The persistent form (pipe3.cuh).  Returns -1 when it does not apply (no instance, unaligned user planes).
+template <typename T>
+int run_q4(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, int by_column, double p0, double p1,
+           long long batch, cudaStream_t s) {
+    const Q4Ops<T>* ops = q4_of<T>(p);
+    if (ops == nullptr) return -1;
+    // bulk copies of the user rows need 16-byte aligned planes
+    if (!stages[0].in_ring && (reinterpret_cast<uintptr_t>(stages[0].in) & 15) != 0) return -1;
+    const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
+    const int tiles = ops->tiles;
+    // items a CTA holds: the one in work plus its landing buffers; the lag between the stages of a beam covers
+    // every item that can be held anywhere (with a margin), so that dependencies are complete when they are checked
+    const int hints = p->pipe_hints >= 0 ? p->pipe_hints : P2_HINT_KEEP_RING;    // (late draw: slower, r2g_sweep1024.log)
+    const long long conc = (long long)p->num_sms * p->q4_ctas * (ops->nbuf + ((hints & P2_HINT_LATE_DRAW) ? 0 : 1));
+    const long long reach = (5 * conc) / 4;
+    int lag = p->q4_lag > 0 ? p->q4_lag : (int)((reach + (long long)nstages * tiles - 1) / ((long long)nstages * tiles));
+    if (lag < 1) lag = 1;
+    const int slots = nstages * lag;
+    if ((long long)slots * plane > p->ring_bytes) return -1;
+    int rc = p2_claim_stream(p, s);
+    if (rc) return rc;
+    if (fac_kind != P2_FAC_NONE) {
+        rc = p2_ensure_factor<T>(p, fac_kind, by_column, p0, p1, s);
+        if (rc) return rc;
+    }
+    const long long groups_cap = (p->counters_cap - 1) / nstages;
+    for (long long b0 = 0; b0 < batch; b0 += groups_cap) {
+        const long long nb = (batch - b0 < groups_cap) ? batch - b0 : groups_cap;
+        P2Args<T> a;
+        memset(&a, 0, sizeof a);
+        const long long off = b0 * (long long)p->n * p->n;
+        for (int i = 0; i < nstages; ++i) {
+            a.st[i] = stages[i];
+            P2Stage<T>& st = a.st[i];
+            if (st.in) st.in += off;
+            if (st.out) st.out += off;
+            if (st.out_pre) st.out_pre += off;
+            if (st.out_mid) st.out_mid += off;
+            if (st.inten) st.inten += off;
+            if (st.mask) st.mask = static_cast<const char*>(st.mask) + b0 * st.mask_beam_stride *
+                                   (st.mask_kind == MASK_CX ? sizeof(cx<T>) : st.mask_kind == MASK_REAL ? sizeof(T) : 1);
+        }
+        a.ring = static_cast<cx<T>*>(p->ring);
+        a.tw = static_cast<const cx<T>*>(p->p2_tw);
+        a.fac = static_cast<const cx<T>*>(p->p2_fac);
+        a.counters = p->counters + (size_t)p->counter_set * p->counters_cap;
+        a.zero_counters = p->counters + (size_t)(p->counter_set ^ 1) * p->counters_cap;
+        a.zero_count = p->counters_used[p->counter_set ^ 1];
+        a.nbeams = nb;
+        a.nstages = nstages;
+        a.ngroups = (int)nb;
+        a.G = 1; a.lag = lag; a.ring_slots = slots;
+        a.fac_map = fac_kind == P2_FAC_LENS ? (p->x2_even ? P2_MAP_CENTRE : P2_MAP_FULL) : P2_MAP_FREQ;
+        a.fac_stride = (fac_kind == P2_FAC_LENS && !p->x2_even) ? p->n : ops->fl;
+        a.hints = hints;
+        a.use_tma = 1;
+        const int box_rows = p->n < 256 ? p->n : 256;
+        if (!encode_plane_map(&a.tm_ring, p->ring, p->n, (long long)slots, (int)sizeof(cx<T>), ops->w, box_rows))
+            return fail(LP2D_ECUDA, "fused step: cuTensorMapEncodeTiled failed");
+        const long long total = ((long long)a.ngroups + (long long)(nstages - 1) * lag) * nstages * tiles;
+        if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "fused step: batch too large for one launch");
+        a.total_items = (int)total;
+        const long long real_items = (long long)a.ngroups * nstages * tiles;
+        long long grid = (long long)p->num_sms * p->q4_ctas;
+        if (grid > real_items) grid = real_items;
+        LP2D_CU(ops->launch(a, (unsigned)grid, s), "fused step launch");
+        p->counters_used[p->counter_set ^ 1] = 0;
+        p->counters_used[p->counter_set] = 1 + nstages * a.ngroups;
+        p->counter_set ^= 1;
+    }
+    return LP2D_OK;
+}
+
 template <typename T>
 int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, int by_column, double p0, double p1,
-           long long batch, cudaStream_t s) {
+           long long batch, cudaStream_t s, int op_bit) {
     const P2Ops<T>* ops = p2_of<T>(p);
     if (ops == nullptr) return -1;
     if (fac_kind == P2_FAC_H && !p->h_even) return -1;      // the folded H plane needs even tables: one kernel per pass
+    if (p->q4_ops & op_bit) {
+        const int rc = run_q4<T>(p, stages, nstages, fac_kind, by_column, p0, p1, batch, s);
+        if (rc != -1) return rc;
+    }
     const bool need_factor = fac_kind != P2_FAC_NONE;
     const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
     const int ctas = need_factor ? p->p2_ctas_factor : p->p2_ctas_plain;
@@ -592,7 +722,7 @@ int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const v
         if (mask != nullptr) { st[0].mask = mask; st[0].mask_kind = mask_kind; st[0].mask_beam_stride = mask_stride; }
         st[1].in_ring = 1;
         st[1].out = static_cast<cx<T>*>(other);
-        const int rc = (p->fused_ops & (state_out != nullptr ? 2 : 1)) ? run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s) : -1;
+        const int rc = (p->fused_ops & (state_out != nullptr ? 2 : 1)) ? run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s, state_out != nullptr ? 2 : 1) : -1;
         if (rc >= 0) return rc;
     }
     const long long plane = (long long)p->n * p->n;
@@ -642,7 +772,7 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         st[1].in_ring = 1;
         st[1].out = static_cast<cx<T>*>(field);
         st[1].inten = static_cast<T*>(intensity);
-        const int rc = (p->fused_ops & 2) ? run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s) : -1;
+        const int rc = (p->fused_ops & 2) ? run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s, 2) : -1;
         if (rc >= 0) return rc;
     }
     const long long plane = (long long)p->n * p->n;
@@ -687,7 +817,7 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
         st[2].in_ring = 1;
         st[2].out = static_cast<cx<T>*>(fout);
         st[2].inten = static_cast<T*>(intensity);
-        const int rc = (p->fused_ops & 4) ? run_p2<T>(p, st, 3, P2_FAC_H, 1, z, 0.0, batch, s) : -1;
+        const int rc = (p->fused_ops & 4) ? run_p2<T>(p, st, 3, P2_FAC_H, 1, z, 0.0, batch, s, 4) : -1;
         if (rc >= 0) return rc;
     }
     const long long plane = (long long)p->n * p->n;

@@ -7,14 +7,37 @@
 
 namespace lp2d {
 static const P2Ops<float> kP2F32[] = {
+    // 2048 points: a line is two warps (E = 32), 4 lines per CTA; a plane is 32 MB: the ring (2 planes) only partly
+    // stays in L2 (opt-in: LP2D_FUSED_OPS)
+    T3Inst<float, 2048, 32, 4, 2, 3>::entry(),
+    T3Inst<float, 2048, 32, 4, 2>::entry(),
     // the first entry of each size is the default (measured best, profiles/r1c_size_sweep.log)
-    T3Inst<float, 1024, 32, 8, 2>::entry(),
+    T3Inst<float, 1024, 32, 8, 2, 3>::entry(),
+    T3Inst<float, 1024, 32, 8, 2, 0>::entry(),
     T3Inst<float, 1024, 32, 4, 3>::entry(),
     T3Inst<float, 512, 32, 8, 3>::entry(),
     T3Inst<float, 512, 32, 16, 2>::entry(),
     T3Inst<float, 256, 16, 16, 4>::entry(),
     T3Inst<float, 256, 16, 8, 8>::entry(),
 };
+static const Q4Ops<float> kQ4F32[] = {
+    Q4Inst<float, 1024, 32, 8, 2, 2>::entry(),
+    Q4Inst<float, 1024, 32, 8, 2, 3>::entry(),
+    Q4Inst<float, 1024, 32, 8, 2, 0>::entry(),
+    Q4Inst<float, 512, 32, 16, 2>::entry(),
+    Q4Inst<float, 512, 32, 16, 1>::entry(),
+    Q4Inst<float, 256, 16, 16, 2>::entry(),
+};
+const Q4Ops<float>* find_q4_f32(int n, int variant) {
+    const Q4Ops<float>* first = nullptr;
+    int seen = 0;
+    for (const auto& o : kQ4F32) {
+        if (o.n != n) continue;
+        if (seen++ == variant) return &o;
+        if (first == nullptr) first = &o;
+    }
+    return first;
+}
 const P2Ops<float>* find_p2_f32(int n, int variant) {
     const P2Ops<float>* first = nullptr;
     int seen = 0;

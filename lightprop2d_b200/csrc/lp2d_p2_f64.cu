@@ -3,11 +3,25 @@
 
 namespace lp2d {
 static const P2Ops<double> kP2F64[] = {
+    // 1024 points: a line is two warps (E = 16), 4 lines per CTA; a plane is 16 MB, the ring holds 2-3 of them
+    T3Inst<double, 1024, 16, 4, 1>::entry(),
+    T3Inst<double, 1024, 16, 2, 3>::entry(),
+    T3Inst<double, 1024, 16, 4, 1, 3>::entry(),
     T3Inst<double, 512, 16, 4, 3>::entry(),
     T3Inst<double, 512, 16, 8, 2>::entry(),
     T3Inst<double, 256, 16, 8, 3>::entry(),
     T3Inst<double, 256, 8, 8, 4>::entry(),
 };
+static const Q4Ops<double> kQ4F64[] = {
+    Q4Inst<double, 512, 16, 8, 2>::entry(),
+    Q4Inst<double, 256, 16, 16, 2>::entry(),
+};
+const Q4Ops<double>* find_q4_f64(int n, int variant) {
+    (void)variant;
+    for (const auto& o : kQ4F64)
+        if (o.n == n) return &o;
+    return nullptr;
+}
 const P2Ops<double>* find_p2_f64(int n, int variant) {
     const P2Ops<double>* first = nullptr;
     int seen = 0;

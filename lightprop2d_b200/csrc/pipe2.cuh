@@ -97,7 +97,8 @@ __device__ __forceinline__ void p2_signal_consumed(unsigned int* ctr) {
 }
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
 enum { P2_HINT_KEEP_RING = 2,        // bit 0 was the (dropped) hint on the cp.async path
-       P2_HINT_PREFETCH = 4 };       // speculative L2 prefetch of the user rows of item blockIdx.x while the ticket is drawn
+       P2_HINT_PREFETCH = 4,         // speculative L2 prefetch of the user rows of item blockIdx.x while the ticket is drawn
+       P2_HINT_LATE_DRAW = 8 };      // persistent form: draw the next ticket when an item is finished, not when its tile is read
 // KIND is a compile-time value: a policy selected at run time ends up in a misaligned uniform
 // register pair (ptxas 12.9) and the copy traps as an illegal instruction.
 template <int KIND>     // 0 no hint, 1 evict first, 2 evict last
@@ -212,7 +213,7 @@ struct T3Cfg {
     static_assert(THREADS >= 32 && THREADS <= 1024, "block size");
 };
 
-template <typename T, int N, int E, int W, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+template <typename T, int N, int E, int W, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
 __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, int tid) {
     using K = T3Cfg<T, N, E, W>;
     constexpr int TPL = K::TPL;
@@ -261,14 +262,33 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
                     if (E > 16) asm volatile("" ::: "memory");
                 }
             }
-            if (st.out_pre != nullptr) {
-                cx<T>* dst = st.out_pre + b * PLANE + off0 + t * PSTRIDE;
-#pragma unroll
-                for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
-            }
         }
-        line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+        // The global stores ride on the butterflies (hooks of dft_reg): the state goes out while the first radix pass
+        // consumes it, the result while the last radix pass produces it (a burst of 32 stores per thread fills the
+        // load/store queue: lg_throttle was the second stall reason in profiles/r1d_ncu_full_t3_default_summary.txt).
+        cx<T>* const pre_dst = (!IN_RING && st.out_pre != nullptr) ? st.out_pre + b * PLANE + off0 + t * PSTRIDE : nullptr;
+        auto pre_hook = [&](int m, const cx<T>& val) {
+            if (pre_dst != nullptr) __stcs(pre_dst + (TPL * m) * PSTRIDE, val);
+        };
+        cx<T>* const ring_dst = OUT_RING ? p.ring + (slot0 + bi) * PLANE + off0 : nullptr;
+        cx<T>* const out_dst = (!OUT_RING && st.out != nullptr) ? st.out + b * PLANE + off0 : nullptr;
+        T* const inten_dst = (!OUT_RING && st.inten != nullptr) ? st.inten + b * PLANE + off0 : nullptr;
+        const T scale = st.scale;
+        auto post_hook = [&](int m, const cx<T>& val0) {
+            const cx<T> val = cscale(val0, scale);          // (a scale of 1 is exact)
+            const long long o = (m == 0) ? o_first : o_base + m * o_step;
+            if constexpr (OUT_RING) {
+                if (keep_ring) p2_st_ring<2>(ring_dst + o, val);
+                else p2_st_ring<0>(ring_dst + o, val);
+            } else {
+                if (out_dst != nullptr) __stcs(out_dst + o, val);
+                if (inten_dst != nullptr) __stcs(inten_dst + o, val.x * val.x + val.y * val.y);
+            }
+        };
+        // HOOKS bit 0: state stores inside the first radix pass, bit 1: result stores inside the last one; otherwise
+        // bursts (measured per size, profiles/r2g_sweep*.log: hooks win at 1024 points, bursts at 512)
         if constexpr (MID) {
+            line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = cmul(v[m], __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]));
             if (st.out_mid != nullptr) {
@@ -276,40 +296,21 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
 #pragma unroll
                 for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
             }
-            line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
-        }
-        if (st.scale != (T)1) {
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = cscale(v[m], st.scale);
-        }
-        if constexpr (OUT_RING) {
-            cx<T>* dst = p.ring + (slot0 + bi) * PLANE + off0;
-            if (keep_ring) {
-                p2_st_ring<2>(dst + o_first, v[0]);
-                dst += o_base;
-#pragma unroll
-                for (int m = 1; m < E; ++m) p2_st_ring<2>(dst + m * o_step, v[m]);
-            } else {
-                p2_st_ring<0>(dst + o_first, v[0]);
-                dst += o_base;
-#pragma unroll
-                for (int m = 1; m < E; ++m) p2_st_ring<0>(dst + m * o_step, v[m]);
-            }
+            if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, NoHook(), post_hook);
+            else line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
         } else {
-            if (st.out != nullptr) {
-                cx<T>* dst = st.out + b * PLANE + off0;
-                __stcs(dst + o_first, v[0]);
-                dst += o_base;
+            if constexpr (!IN_RING && (HOOKS & 1) == 0) {
 #pragma unroll
-                for (int m = 1; m < E; ++m) __stcs(dst + m * o_step, v[m]);
+                for (int m = 0; m < E; ++m) pre_hook(m, v[m]);
             }
-            if (st.inten != nullptr) {
-                T* dst = st.inten + b * PLANE + off0;
-                __stcs(dst + o_first, v[0].x * v[0].x + v[0].y * v[0].y);
-                dst += o_base;
+            if constexpr (!IN_RING && (HOOKS & 1) != 0 && (HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, pre_hook, post_hook);
+            else if constexpr (!IN_RING && (HOOKS & 1) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, pre_hook, NoHook());
+            else if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, NoHook(), post_hook);
+            else line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+        }
+        if constexpr ((HOOKS & 2) == 0) {
 #pragma unroll
-                for (int m = 1; m < E; ++m) __stcs(dst + m * o_step, v[m].x * v[m].x + v[m].y * v[m].y);
-            }
+            for (int m = 0; m < E; ++m) post_hook(m, v[m]);
         }
     }
 }
@@ -421,7 +422,7 @@ __device__ __forceinline__ void t3_col_tma_item(const P2Args<T>& p, const P2Item
     // bulk stores complete before the grid does
 }
 
-template <typename T, int N, int E, int W, int MINB>
+template <typename T, int N, int E, int W, int MINB, int HOOKS>
 __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(const __grid_constant__ P2Args<T> p) {
     using K = T3Cfg<T, N, E, W>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -484,16 +485,16 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
         P2Item it;
         p2_decode<T, K::TILES>(p, item, it);
         if (it.s == 0) {
-            if (p.st[0].inverse) t3_item<T, N, E, W, 0, AX_ROW, false, true, false, true>(p, it, xbuf, tid);
-            else t3_item<T, N, E, W, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
+            if (p.st[0].inverse) t3_item<T, N, E, W, HOOKS, 0, AX_ROW, false, true, false, true>(p, it, xbuf, tid);
+            else t3_item<T, N, E, W, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
         } else if (it.s == 1) {
-            if (p.st[1].mid) t3_item<T, N, E, W, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
+            if (p.st[1].mid) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
             else if (p.use_tma && p.st[1].inverse) t3_col_tma_item<T, N, E, W, true>(p, it, xbuf, &s_bar, tma_parity, tid);
             else if (p.use_tma) t3_col_tma_item<T, N, E, W, false>(p, it, xbuf, &s_bar, tma_parity, tid);
-            else if (p.st[1].inverse) t3_item<T, N, E, W, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
-            else t3_item<T, N, E, W, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
+            else if (p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
+            else t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
         } else {
-            t3_item<T, N, E, W, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
+            t3_item<T, N, E, W, HOOKS, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
         }
         __syncthreads();                                   // all stores of the item are issued
         if (tid == 0) {

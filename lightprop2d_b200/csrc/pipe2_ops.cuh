@@ -3,7 +3,7 @@
 #include <cmath>
 #include <cuda_runtime.h>
 #include <vector>
-#include "pipe2.cuh"
+#include "pipe3.cuh"
 
 namespace lp2d {
 
@@ -23,6 +23,20 @@ struct P2Ops {
     cudaError_t (*configure)(int* ctas_per_sm_factor, int* ctas_per_sm_plain);
     void (*twiddles)(std::vector<double>& re_im);
 };
+
+// persistent form (pipe3.cuh, q4_kernel): same arguments, one CTA per SM
+template <typename T>
+struct Q4Ops {
+    int n, e, w;
+    int tiles, threads, fl, tw_size;
+    size_t smem;
+    int nbuf;           // landing buffers per CTA (items a CTA holds besides the one it works on)
+    cudaError_t (*launch)(const P2Args<T>& a, unsigned grid, cudaStream_t s);
+    cudaError_t (*configure)(int* ctas_per_sm);
+    void (*twiddles)(std::vector<double>& re_im);
+};
+const Q4Ops<float>* find_q4_f32(int n, int variant);
+const Q4Ops<double>* find_q4_f64(int n, int variant);
 
 const P2Ops<float>* find_p2_f32(int n, int variant);
 const P2Ops<double>* find_p2_f64(int n, int variant);
@@ -49,17 +63,17 @@ void p2_twiddles(std::vector<double>& w) {
     }
 }
 
-template <typename T, int N, int E, int W, int MINB>
+template <typename T, int N, int E, int W, int MINB, int HOOKS = 0>
 struct T3Inst {
     using K = T3Cfg<T, N, E, W>;
     using LP = LinePlan<N, E>;
     static cudaError_t launch(const P2Args<T>& a, unsigned grid, bool, cudaStream_t s, void*, size_t) {
-        t3_kernel<T, N, E, W, MINB><<<grid, K::THREADS, K::SMEM_X, s>>>(a);
+        t3_kernel<T, N, E, W, MINB, HOOKS><<<grid, K::THREADS, K::SMEM_X, s>>>(a);
         ++g_launches;
         return cudaGetLastError();
     }
     static cudaError_t configure(int* with_factor, int* plain) {
-        auto kern = t3_kernel<T, N, E, W, MINB>;
+        auto kern = t3_kernel<T, N, E, W, MINB, HOOKS>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM_X);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(with_factor, kern, K::THREADS, K::SMEM_X);
@@ -69,6 +83,27 @@ struct T3Inst {
     static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
     static constexpr P2Ops<T> entry() {
         return P2Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM_X, 0, &launch, &configure, &twiddles};
+    }
+};
+
+template <typename T, int N, int E, int W, int NBUF, int HOOKS = 2>
+struct Q4Inst {
+    using K = Q4Cfg<T, N, E, W, NBUF>;
+    using LP = LinePlan<N, E>;
+    static cudaError_t launch(const P2Args<T>& a, unsigned grid, cudaStream_t s) {
+        q4_kernel<T, N, E, W, NBUF, HOOKS><<<grid, K::THREADS, K::SMEM, s>>>(a);
+        ++g_launches;
+        return cudaGetLastError();
+    }
+    static cudaError_t configure(int* ctas) {
+        auto kern = q4_kernel<T, N, E, W, NBUF, HOOKS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, K::THREADS, K::SMEM);
+    }
+    static void twiddles(std::vector<double>& w) { p2_twiddles<LP>(w); }
+    static constexpr Q4Ops<T> entry() {
+        return Q4Ops<T>{N, E, W, K::TILES, K::THREADS, K::FL, LP::tw_size(), K::SMEM, NBUF, &launch, &configure, &twiddles};
     }
 };
 

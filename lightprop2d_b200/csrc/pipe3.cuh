@@ -1,0 +1,379 @@
+// The persistent form of the fused step kernel ("Q4"): same work items, same L2-resident ring, same ticket order and
+// dependency counters as t3_kernel (pipe2.cuh), but memory movement is decoupled from the transform warps.
+//
+// One CTA per SM, alive for the whole launch:
+//   * consumer warps (W * N / E threads): run the register-resident line transform of fft_core.cuh on a tile that is
+//     ALREADY in shared memory, and store the results straight from registers;
+//   * one producer thread: draws the tickets, checks the dependencies (without stalling the consumers), and has the
+//     tile of the NEXT item copied into a free landing buffer by the copy engines: row tiles (W consecutive grid rows
+//     are W*N*sizeof contiguous bytes) with `cp.async.bulk` (UBLKCP), column tiles (N rows of W*sizeof bytes) with
+//     `cp.async.bulk.tensor.2d` (UTMALDG) -- the TMA unit gathers the 64/128-byte pieces, no LSU wavefronts are spent;
+//   * one signaller thread: publishes the completion counter of an item (`red.release.gpu`) once every consumer warp
+//     has issued its stores, so that no transform warp ever sits in a release fence.
+// Landing buffers cycle through full / empty mbarriers (expect_tx + complete_tx); a buffer is released as soon as its
+// samples are in registers, i.e. the copy of item k+2 runs while item k is still being transformed and stored.  Hence
+// every SM keeps 64-128 KB of loads in flight all the time, whatever the consumers are doing -- the t3 form had two
+// CTAs per SM that each went load -> transform -> store in sequence (23 % of the warp slots active).
+//
+// Row items never need a CTA-wide exchange: one line belongs to one warp (1024 points, E = 32), its exchange region in
+// shared memory is private.  Column items exchange across the consumer warps through a named barrier that the
+// producer / signaller threads are not part of.
+#pragma once
+#include "pipe2.cuh"
+
+namespace lp2d {
+
+enum { Q4_NDONE = 4 };       // (named barrier 15 belongs to the consumer threads, fft_core.cuh)
+
+template <typename T, int N, int E, int W, int NBUF>
+struct Q4Cfg {
+    using P = LinePlan<N, E>;
+    static constexpr int TPL = P::TPL;
+    static constexpr int NCT = TPL * W;                    // consumer threads
+    static constexpr int NCW = NCT / 32;                   // consumer warps
+    static constexpr int THREADS = NCT + 64;               // + producer warp + signaller warp
+    static constexpr int TILES = N / W;
+    static constexpr int SZ = (int)sizeof(cx<T>);
+    static constexpr int S128 = 128 / SZ;
+    static constexpr int WANT = (W >= S128) ? 1 : S128 / W;
+    static constexpr int LS = P::LINE_SLOTS + ((WANT - P::LINE_SLOTS % S128) + S128) % S128;
+    static constexpr int TILE_BYTES = W * N * SZ;
+    static constexpr size_t SMEM_X = (size_t)W * LS * SZ;
+    static constexpr size_t SMEM_TW = ((size_t)P::tw_size() * SZ + 127) / 128 * 128;   // twiddle table, copied in once
+    static constexpr size_t SMEM = (size_t)NBUF * TILE_BYTES + SMEM_X + SMEM_TW;
+    static constexpr int SYNC_ROW = (TPL <= 32) ? SYNC_WARP : SYNC_NAMED;
+    static constexpr int BOX = (N < 256) ? N : 256;        // rows per TMA box of a column tile
+    static constexpr int FL = N / 2 + 2;
+    static_assert(NCT == LP2D_Q4_CONSUMER_THREADS, "the consumer barrier is compiled for 256 threads");
+    static_assert(NCT % 32 == 0 && (W * SZ) % 16 == 0 && W <= 256, "tile shape");
+    static_assert(TPL <= 32 || (TPL % 32 == 0 && W <= 14), "named row barriers");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+__device__ __forceinline__ void q4_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p2_smem_u32(bar)) : "memory");
+}
+// wait of a helper thread: it has nothing to do meanwhile and must not take issue slots from the transform warps of its
+// scheduler, so it sleeps between the tests
+__device__ __forceinline__ void q4_mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = p2_smem_u32(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(128);
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void q4_consumer_barrier() {
+    asm volatile("bar.sync 15, %0;" ::"n"(LP2D_Q4_CONSUMER_THREADS) : "memory");
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier; the source is read once (evict first)
+__device__ __forceinline__ void q4_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, bool stream) {
+    if (stream) {
+        const unsigned long long pol = p2_policy<1>();
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         p2_smem_u32(smem_dst)),
+                     "l"(gsrc), "r"(bytes), "r"(p2_smem_u32(bar)), "l"(pol)
+                     : "memory");
+    } else {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(p2_smem_u32(smem_dst)),
+                     "l"(gsrc), "r"(bytes), "r"(p2_smem_u32(bar))
+                     : "memory");
+    }
+}
+
+// Row item, tile in registers: the warp hands its part of the landing buffer back.  The exchange region of a line is
+// private to its warp in row items, but the threads of a COLUMN item's line are spread over all warps: the first row
+// item after a column item waits until every warp has left that item's last gather.
+__device__ __forceinline__ void q4_row_release(uint64_t* empty_bar, int ctid, bool after_column_item) {
+    if (after_column_item) q4_consumer_barrier();
+    else __syncwarp();
+    if ((ctid & 31) == 0) q4_mbar_arrive(empty_bar);
+}
+
+// Dependency wait of the producer: relaxed polls (an acquire load invalidates the SM's L1 every time), then ONE
+// acquire read of the same counters once they are complete.
+template <typename T, int TILES>
+__device__ __forceinline__ void q4_wait_ready(const P2Args<T>& p, int item, unsigned int full) {
+    P2Item it;
+    p2_decode<T, TILES>(p, item, it);
+    const unsigned int* done = p.counters + 1;
+    const P2Stage<T>& st = p.st[it.s];
+    const unsigned int* ca = (it.s > 0) ? &done[(it.s - 1) * p.ngroups + it.g] : nullptr;
+    const unsigned int* cb = (st.out_ring && !st.in_ring && it.g >= p.ring_slots)
+                                 ? &done[(p.nstages - 1) * p.ngroups + (it.g - p.ring_slots)] : nullptr;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned int va = full, vb = full;
+        if (ca) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(va) : "l"(ca) : "memory");
+        if (cb) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(vb) : "l"(cb) : "memory");
+        if (va >= full && vb >= full) break;
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    if (ca) (void)p2_ld_relaxed(ca);                       // (named "relaxed" for history: it is ld.acquire.gpu)
+    if (cb) (void)p2_ld_relaxed(cb);
+}
+
+// One item on the consumer threads.  `land` holds the tile: rows as [line][N] (dense), columns as [row][W].
+template <typename T, int N, int E, int W, int NBUF, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+__device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, const cx<T>* __restrict__ land, cx<T>* xbuf,
+                                        const cx<T>* __restrict__ stw, uint64_t* empty_bar, int ctid, bool after_column_item) {
+    using K = Q4Cfg<T, N, E, W, NBUF>;
+    constexpr int TPL = K::TPL;
+    constexpr long long PLANE = (long long)N * N;
+    constexpr long long PSTRIDE = (AXIS == AX_ROW) ? 1 : N;
+    constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CONSUMERS;
+    constexpr bool REV = MID || INV;
+    const P2Stage<T>& st = p.st[S];
+    const int l = (AXIS == AX_ROW) ? ctid / TPL : ctid % W;
+    const int t = (AXIS == AX_ROW) ? ctid % TPL : ctid / W;
+    cx<T>* sline = xbuf + l * K::LS;
+    const long long b = it.g;                              // one beam per group
+    const long long slot = it.g % p.ring_slots;
+    const int fixed = it.tile * W + l;
+    const long long off0 = (AXIS == AX_ROW) ? (long long)fixed * N : fixed;
+    const long long o_first = (REV ? (long long)((N - t) & (N - 1)) : (long long)t) * PSTRIDE;
+    const long long o_base = (REV ? (long long)(N - t) : (long long)t) * PSTRIDE;
+    constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * PSTRIDE;
+    const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
+    const cx<T>* fline = p.fac + (long long)fixed * p.fac_stride;      // L2-resident factor row of this line
+    const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
+
+    cx<T> v[E];
+    if (use_pre) {
+        // the factors come from L2 (a few hundred cycles): ask for all of them before the tile is touched
+        cx<T> h[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) h[m] = __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]);
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
+        if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
+        if (st.mask_kind != MASK_NONE) {
+            const long long mb = b * st.mask_beam_stride + off0;
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
+        }
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], h[m]);
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
+        if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
+        if constexpr (!IN_RING) {
+            if (st.mask_kind != MASK_NONE) {
+                const long long mb = b * st.mask_beam_stride + off0;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
+            }
+        }
+    }
+    // The global stores ride on the butterflies (hooks of dft_reg): the state (spectrum * H, field * lens ...) goes out
+    // while the first radix pass consumes it, the result while the last radix pass produces it.
+    cx<T>* const pre_dst = (!IN_RING && st.out_pre != nullptr) ? st.out_pre + b * PLANE + off0 + t * PSTRIDE : nullptr;
+    auto pre_hook = [&](int m, const cx<T>& val) {
+        if (pre_dst != nullptr) __stcs(pre_dst + (TPL * m) * PSTRIDE, val);
+    };
+    cx<T>* const ring_dst = OUT_RING ? p.ring + slot * PLANE + off0 : nullptr;
+    cx<T>* const out_dst = (!OUT_RING && st.out != nullptr) ? st.out + b * PLANE + off0 : nullptr;
+    T* const inten_dst = (!OUT_RING && st.inten != nullptr) ? st.inten + b * PLANE + off0 : nullptr;
+    const T scale = st.scale;
+    auto post_hook = [&](int m, const cx<T>& val0) {
+        const cx<T> val = cscale(val0, scale);              // (a scale of 1 is exact)
+        const long long o = (m == 0) ? o_first : o_base + m * o_step;
+        if constexpr (OUT_RING) {
+            p2_st_ring<2>(ring_dst + o, val);              // L2 evict-last: the ring is re-read by the next stage
+        } else {
+            if (out_dst != nullptr) __stcs(out_dst + o, val);
+            if (inten_dst != nullptr) __stcs(inten_dst + o, val.x * val.x + val.y * val.y);
+        }
+    };
+    // HOOKS bit 0: state stores inside the first radix pass, bit 1: result stores inside the last one; otherwise bursts
+    auto pre_burst = [&]() {
+        if (!(HOOKS & 1)) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) pre_hook(m, v[m]);
+        }
+    };
+    auto post_burst = [&]() {
+        if (!(HOOKS & 2)) {
+#pragma unroll
+            for (int m = 0; m < E; ++m) post_hook(m, v[m]);
+        }
+    };
+    if constexpr (MID) {
+        line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l);
+        if ((ctid & 31) == 0) q4_mbar_arrive(empty_bar);   // every thread passed the first exchange barrier
+#pragma unroll
+        for (int m0 = 0; m0 < E; m0 += 8) {
+            cx<T> h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (m0 + i < E) h[i] = __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * (m0 + i), m0 + i)]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (m0 + i < E) v[m0 + i] = cmul(v[m0 + i], h[i]);
+        }
+        if (st.out_mid != nullptr) {
+            cx<T>* dst = st.out_mid + b * PLANE + off0 + t * PSTRIDE;
+#pragma unroll
+            for (int m = 0; m < E; ++m) __stcs(dst + (TPL * m) * PSTRIDE, v[m]);
+        }
+        if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, NoHook(), post_hook);
+        else line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l);
+        post_burst();
+    } else {
+        if constexpr (!IN_RING) pre_burst();
+        if constexpr (!IN_RING && (HOOKS & 1) != 0 && (HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, pre_hook, post_hook);
+        else if constexpr (!IN_RING && (HOOKS & 1) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, pre_hook, NoHook());
+        else if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, NoHook(), post_hook);
+        else line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l);
+        if (AXIS == AX_COL && (ctid & 31) == 0) q4_mbar_arrive(empty_bar);
+        post_burst();
+    }
+}
+
+template <typename T, int N, int E, int W, int NBUF, int HOOKS>
+__global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel(const __grid_constant__ P2Args<T> p) {
+    using K = Q4Cfg<T, N, E, W, NBUF>;
+    constexpr int Q4_NBUF = NBUF;
+    // (no pointer arithmetic through integers on this array: the compiler must keep seeing shared-memory addresses,
+    // or every tile access becomes a generic LD / ST that queues with the global accesses)
+    extern __shared__ __align__(1024) unsigned char q4_smem_raw[];
+    __shared__ uint64_t s_full[Q4_NBUF], s_empty[Q4_NBUF], s_done[Q4_NDONE];
+    __shared__ int s_desc[Q4_NBUF], s_done_item[Q4_NDONE];
+    __shared__ volatile unsigned int s_signalled;
+    unsigned char* smem = q4_smem_raw;
+    cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem + (size_t)Q4_NBUF * K::TILE_BYTES);
+    cx<T>* stw = reinterpret_cast<cx<T>*>(smem + (size_t)Q4_NBUF * K::TILE_BYTES + K::SMEM_X);
+    const int tid = threadIdx.x;
+    // the twiddle table lives in shared memory: the producer's acquire loads invalidate L1 all the time
+    for (int i = tid; i < K::P::tw_size(); i += K::THREADS) stw[i] = p.tw[i];
+
+    if (tid == 0) {
+        for (int i = 0; i < Q4_NBUF; ++i) {
+            p2_mbar_init(&s_full[i], 1);
+            p2_mbar_init(&s_empty[i], K::NCW);
+        }
+        for (int i = 0; i < Q4_NDONE; ++i) p2_mbar_init(&s_done[i], K::NCW);
+        s_signalled = 0u;
+    }
+    // zero the counter set of the previous launch (it is next used by the launch after this one)
+    for (unsigned int i = blockIdx.x * K::THREADS + tid; i < (unsigned int)p.zero_count; i += gridDim.x * K::THREADS)
+        p.zero_counters[i] = 0u;
+    __syncthreads();
+
+    if (tid >= K::NCT) {
+        const int h = tid - K::NCT;
+        if (h == 0) {
+            // ------------------------------------------------------------------ producer
+            for (unsigned int k = 0;; ++k) {
+                int item;
+                P2Item it;
+                for (;;) {                                  // fill / drain numbers of the schedule carry no work
+                    item = (int)atomicAdd(&p.counters[0], 1u);
+                    if (item >= p.total_items) { item = -1; break; }
+                    if (p2_decode<T, K::TILES>(p, item, it)) break;
+                }
+                const int buf = (int)(k % Q4_NBUF);
+                if (k >= Q4_NBUF) {
+                    q4_mbar_wait_idle(&s_empty[buf], ((k / Q4_NBUF) - 1u) & 1u);
+                    // "late draw": the next ticket is taken only when item k - NBUF has left the CTA altogether (all its
+                    // stores issued), not as soon as its tile is in registers.  The CTA then holds two unfinished items
+                    // instead of three, the lag between the stages of a beam can be one group shorter, and the ring
+                    // (stages * lag planes) fits the part of L2 that keeps it resident.  Lead time of the copy: one item.
+                    if (p.hints & P2_HINT_LATE_DRAW) {
+                        const unsigned int j = k - Q4_NBUF;
+                        q4_mbar_wait_idle(&s_done[j % Q4_NDONE], (j / Q4_NDONE) & 1u);
+                    }
+                }
+                if (k >= Q4_NDONE) {                        // slot k % NDONE of the completion ring is free again
+                    const long long t0 = clock64();
+                    while (s_signalled + Q4_NDONE <= k) {
+                        __nanosleep(128);
+                        if (clock64() - t0 > 4000000000ll) __trap();
+                    }
+                }
+                s_desc[buf] = item;
+                s_done_item[k % Q4_NDONE] = item;
+                if (item < 0) {
+                    q4_mbar_arrive(&s_full[buf]);
+                    break;
+                }
+                q4_wait_ready<T, K::TILES>(p, item, (unsigned)K::TILES);
+                const P2Stage<T>& st = p.st[it.s];
+                unsigned char* land = smem + (size_t)buf * K::TILE_BYTES;
+                // what the copy engines read from the ring was written with ordinary stores by other SMs
+                if (st.in_ring) asm volatile("fence.proxy.async;" ::: "memory");
+                p2_mbar_expect_tx(&s_full[buf], (uint32_t)K::TILE_BYTES);
+                if (st.axis == AX_ROW) {
+                    const cx<T>* src = (st.in_ring ? p.ring + (long long)(it.g % p.ring_slots) * N * N : st.in + (long long)it.g * N * N) +
+                                       (long long)it.tile * W * N;
+                    // W consecutive rows are contiguous; 32 KB pieces keep several requests in flight
+                    constexpr int PIECE = K::TILE_BYTES < 32768 ? K::TILE_BYTES : 32768;
+#pragma unroll
+                    for (int q = 0; q < K::TILE_BYTES / PIECE; ++q)
+                        q4_bulk_load(land + q * PIECE, reinterpret_cast<const unsigned char*>(src) + q * PIECE, PIECE, &s_full[buf], !st.in_ring);
+                } else {
+                    constexpr int FPC = K::SZ / 4;
+#pragma unroll
+                    for (int q = 0; q < N / K::BOX; ++q)
+                        p2_tma_load_2d(land + (size_t)q * K::BOX * W * K::SZ, &p.tm_ring, it.tile * W * FPC,
+                                       (int)((it.g % p.ring_slots) * N) + q * K::BOX, &s_full[buf]);
+                }
+            }
+        } else if (h == 32) {
+            // ----------------------------------------------------------------- signaller
+            for (unsigned int k = 0;; ++k) {
+                q4_mbar_wait_idle(&s_done[k % Q4_NDONE], (k / Q4_NDONE) & 1u);
+                const int item = s_done_item[k % Q4_NDONE];
+                if (item < 0) break;
+                P2Item it;
+                p2_decode<T, K::TILES>(p, item, it);
+                unsigned int* ctr = p.counters + 1 + it.s * p.ngroups + it.g;
+                if (it.s == p.nstages - 1) p2_signal_consumed(ctr);
+                else p2_signal(ctr);
+                s_signalled = k + 1u;
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------------ consumers
+    bool after_col = false;
+    for (unsigned int k = 0;; ++k) {
+        const int buf = (int)(k % Q4_NBUF);
+        p2_mbar_wait(&s_full[buf], (k / Q4_NBUF) & 1u);
+        const int item = s_desc[buf];
+        if (item >= 0) {
+            P2Item it;
+            p2_decode<T, K::TILES>(p, item, it);
+            const cx<T>* land = reinterpret_cast<const cx<T>*>(smem + (size_t)buf * K::TILE_BYTES);
+            uint64_t* eb = &s_empty[buf];
+            if (it.s == 0) {
+                if (p.st[0].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
+                else q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, land, xbuf, stw, eb, tid, after_col);
+            } else if (it.s == 1) {
+                if (p.st[1].mid) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, true, true, false>(p, it, land, xbuf, stw, eb, tid, after_col);
+                else if (p.st[1].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
+                else q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, false>(p, it, land, xbuf, stw, eb, tid, after_col);
+            } else {
+                q4_item<T, N, E, W, NBUF, HOOKS, 2, AX_ROW, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
+            }
+            after_col = (it.s == 1);
+        }
+        __syncwarp();                                      // the warp's stores of the item are issued
+        if ((tid & 31) == 0) q4_mbar_arrive(&s_done[k % Q4_NDONE]);
+        if (item < 0) break;
+    }
+}
+
+}  // namespace lp2d

@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE ONLY — import the UNMODIFIED reference from /root/reference.
 
-Works only in the build container (the reference mount does not exist on the GPU
-box).  Used by ``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and by
-``tests/test_oracle_vs_reference.py`` (skipped when the mount is absent).
+Source of the package, in this order: the read-only mount ``/root/reference`` (build container;
+``oracle/make_golden.py`` generates ``tests/golden/*.npz`` from it), else ``oracle/_ref`` (the pip
+install of the same unmodified package made by ``oracle/build_ref.py``; git-ignored, it travels to
+the GPU box with the snapshot so that ``bench.py --impl reference`` / ``cpu_baseline`` can time the
+reference's own ``Beam2D`` there).
 
 The reference cannot be imported as is without cupy (``NameError: cp`` at
 beam2d.py:135, annotations are evaluated at def time), so a stub ``cupy`` module
@@ -15,17 +17,30 @@ import sys
 import types
 import warnings
 
-REF_ROOT = "/root/reference"
+REF_MOUNT = "/root/reference"
+REF_INSTALL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def ref_root():
+    for root in (REF_MOUNT, REF_INSTALL):
+        if os.path.isfile(os.path.join(root, "lightprop2d", "beam2d.py")):
+            return root
+    return None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "lightprop2d"))
+    return ref_root() is not None
+
+
+def mount_available() -> bool:
+    return os.path.isfile(os.path.join(REF_MOUNT, "lightprop2d", "beam2d.py"))
 
 
 def load():
     """Return the reference ``lightprop2d`` module (numpy path)."""
-    if not available():
-        raise RuntimeError("reference mount /root/reference is not present")
+    REF_ROOT = ref_root()
+    if REF_ROOT is None:
+        raise RuntimeError("neither the reference mount /root/reference nor oracle/_ref is present")
     import numpy as np
     sys.dont_write_bytecode = True            # the mount is read-only
     if "cupy" not in sys.modules:
