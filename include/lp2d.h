@@ -188,10 +188,48 @@ LP2D_API int lp2d_moments(int dtype, const void* field, int n, double dL, double
 LP2D_API int lp2d_modes_project(int dtype, const void* field, const void* modes, void* coeffs, int n,
                        int nb, int nmodes, long long batch, void* stream);
 
+/* The same projection for a strip of the crop held by one rank of a slab-decomposed grid (SURVEY.md section 8e
+ * row 3): coeffs[k] = sum_{p < count} modes[k * ldm + p] * flat_field[p].  The caller adds the partial vectors of
+ * the ranks (one all-reduce of nmodes complex numbers, lightprop2d_b200/slab.py). */
+LP2D_API int lp2d_modes_project_flat(int dtype, const void* flat_field, const void* modes, void* coeffs,
+                            long long count, long long ldm, int nmodes, void* stream);
+
 /* construct_by_modes (beam2d.py:552-562, 664-666): field_b = sum_k coeffs[b][k] * mode_k
  * zero-padded from nb x nb to the centred window of the n x n grid. */
 LP2D_API int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void* field, int n,
                           int nb, int nmodes, long long batch, void* stream);
+
+/* ---- grids the power-of-two kernel sets do not cover (any npoints; grids above lp2d_max_npoints) ----
+ * The reference accepts every npoints (beam2d.py:299-308) and expand() produces e.g. 82 points
+ * (beam2d.py:385-389).  Such grids run as: pointwise factor kernels + a 2-D DFT by Bluestein's algorithm on
+ * top of the power-of-two lp2d_fft2 (lightprop2d_b200/generic.py), all on the device. */
+
+/* data[b][r][c] *= factor(row0 + r, c) on `batch` slabs of `rows` rows of an n x n plane (any n), in place:
+ *   LP2D_PW_H    exp(i 2 pi (trunc(Kz z) - Kz z)), Kz^2 = a[c] - b[row0 + r], p0 = z      (beam2d.py:485-489)
+ *   LP2D_PW_LENS exp(i (x2[c] + x2[row0 + r]) k0 / (2 f)), p0 = k0, p1 = 2 f              (beam2d.py:508-510)
+ * dev_tabs: DEVICE, 3 n doubles a | b | x2 (lp2d_grid_tables).  FP64 phase, the reference's operation order. */
+#define LP2D_PW_H 1
+#define LP2D_PW_LENS 2
+LP2D_API int lp2d_pointwise(int dtype, void* data, long long batch, int rows, int n, int row0, int kind,
+                   const double* dev_tabs, double p0, double p1, void* stream);
+
+/* data[b][i] *= mask[b * mask_beam_stride + i], i < plane (beam2d.py:338, 369); mask_kind as lp2d_mul_fft2. */
+LP2D_API int lp2d_mul_mask(int dtype, void* data, const void* mask, int mask_kind, long long plane,
+                  long long mask_beam_stride, long long batch, void* stream);
+
+/* iprofile without a plan: out = |field|^2 for `count` samples (beam2d.py:717). */
+LP2D_API int lp2d_intensity_n(int dtype, const void* field, void* out, long long count, void* stream);
+
+/* Bluestein: X = post(ifft2_m(fft2_m(pre(x)) * fft2_m(filter))) is the n x n DFT (forward unscaled, inverse
+ * scaled by 1/n^2, _fft2 / _ifft2 of beam2d.py:207-229) for ANY n, with m = lp2d_bluestein_size(n) a power of
+ * two >= 2n - 1.  pre: (batch, n, n) -> (batch, m, m) chirp multiply + zero pad; filter: the (m, m) wrapped
+ * conjugate chirp (transform it once with lp2d_fft2); post: chirp multiply + crop (+ 1/n^2). */
+LP2D_API int lp2d_bluestein_size(int n);
+LP2D_API int lp2d_bluestein_pre(int dtype, const void* in, void* out, int n, int m, long long batch, int inverse,
+                       void* stream);
+LP2D_API int lp2d_bluestein_post(int dtype, const void* in, void* out, int n, int m, long long batch, int inverse,
+                        void* stream);
+LP2D_API int lp2d_bluestein_filter(int dtype, void* out, int n, int m, int inverse, void* stream);
 
 /* Which kernel family serves the steps of this plan that read and write state (propagate, lens,
  * mask + fft2): 0 = one kernel per pass (row pass, column pass), 1 = the fused step kernel (one

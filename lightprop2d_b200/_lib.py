@@ -14,6 +14,7 @@ C64, C128 = 0, 1
 MASK_COMPLEX, MASK_REAL, MASK_U8 = 1, 2, 3
 AXIS_ROWS, AXIS_COLS = 0, 1
 OP_FFT, OP_H_FFT, OP_FFT_H_IFFT = 0, 1, 2
+PW_H, PW_LENS = 1, 2
 
 # name -> (restype, argtypes); mirrors include/lp2d.h one to one
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
@@ -43,7 +44,15 @@ SIGNATURES = {
     "lp2d_phase": (_i, [_i, _vp, _vp, _ll, _vp]),
     "lp2d_moments": (_i, [_i, _vp, _i, _d, _d, _d, _vp, _vp]),
     "lp2d_modes_project": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "lp2d_modes_project_flat": (_i, [_i, _vp, _vp, _vp, _ll, _ll, _i, _vp]),
     "lp2d_modes_synthesize": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _ll, _vp]),
+    "lp2d_pointwise": (_i, [_i, _vp, _ll, _i, _i, _i, _i, _vp, _d, _d, _vp]),
+    "lp2d_mul_mask": (_i, [_i, _vp, _vp, _i, _ll, _ll, _ll, _vp]),
+    "lp2d_intensity_n": (_i, [_i, _vp, _vp, _ll, _vp]),
+    "lp2d_bluestein_size": (_i, [_i]),
+    "lp2d_bluestein_pre": (_i, [_i, _vp, _vp, _i, _i, _ll, _i, _vp]),
+    "lp2d_bluestein_post": (_i, [_i, _vp, _vp, _i, _i, _ll, _i, _vp]),
+    "lp2d_bluestein_filter": (_i, [_i, _vp, _i, _i, _i, _vp]),
     "lp2d_plan_step_kernel": (_i, [_vp, C.c_char_p, _i]),
     "lp2d_launch_count": (_ll, []),
 }

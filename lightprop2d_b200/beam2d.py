@@ -12,8 +12,10 @@ every call.  ``spectrum`` is materialised lazily (first access, or as a by-produ
 of the first ``propagate``); its value is the one the reference would hold.
 
 Differences a caller can see (all documented in DESIGN.md):
-  * ``npoints`` must be a power of two in [16, 8192] (complex64) / [16, 4096]
-    (complex128); other sizes raise ``NotImplementedError``;
+  * powers of two in [16, 8192] (complex64) / [16, 4096] (complex128) run on the fused / per-pass
+    kernel sets; every other ``npoints`` (the reference accepts any, ``expand`` produces e.g. 82) runs
+    through Bluestein's algorithm on top of them, larger powers of two (up to 32768) through the
+    long-line kernels (``generic.py``) -- all on the device, several times slower per point;
   * with ``use_gpu=True`` the ``field``/``spectrum`` attributes are torch CUDA tensors
     (the analogue of cupy arrays); with ``use_gpu=False`` they are numpy copies, so
     scripts written for the numpy backend run unchanged;
@@ -162,8 +164,24 @@ class Beam2D:
         a_tab = self.k0 ** 2 - self.Kx ** 2            # left-to-right as beam2d.py:308
         b_tab = self.Kx ** 2
         x2_tab = self.X ** 2
-        self._plan = _get_plan(int(self.device), int(self.npoints), self.complex_bits,
-                               self.area_size, self.wl, a_tab, b_tab, x2_tab)
+        n = int(self.npoints)
+        dt = _lib.C64 if self.complex_bits == 64 else _lib.C128
+        pow2 = n >= 1 and (n & (n - 1)) == 0
+        if pow2 and int(self._lib.lp2d_min_npoints()) <= n <= int(self._lib.lp2d_max_npoints(dt)):
+            self._plan = _get_plan(int(self.device), n, self.complex_bits, self.area_size, self.wl, a_tab, b_tab, x2_tab)
+            self._gen = None
+        else:
+            # any other npoints / grids above lp2d_max_npoints: pointwise kernels + a generic 2-D DFT engine
+            from . import generic
+            key = ("gen", int(self.device), n, self.complex_bits, float(self.area_size), float(self.wl), x2_tab.tobytes())
+            eng = _PLAN_CACHE.get(key)
+            if eng is None:
+                if len(_PLAN_CACHE) > 16:
+                    _PLAN_CACHE.clear()
+                eng = generic.make_engine(n, self.complex_bits, int(self.device), a_tab, b_tab, x2_tab)
+                _PLAN_CACHE[key] = eng
+            self._plan = None
+            self._gen = eng
 
     # ------------------------------------------------------------------ host <-> device
     def _np(self, data):
@@ -241,6 +259,9 @@ class Beam2D:
     def _materialise_spectrum(self):
         if self._s is None:
             torch = _torch()
+            if self._gen is not None:
+                self._s = self._gen.fft2(self._f)
+                return
             self._s = torch.empty_like(self._f)
             self._call("lp2d_fft2", self._plan.handle, self._f.data_ptr(), self._s.data_ptr(),
                        self._batch(), 0, self._stream())
@@ -261,6 +282,13 @@ class Beam2D:
             return
         torch = _torch()
         self.z += z
+        if self._gen is not None:
+            self._materialise_spectrum()
+            if self._s.data_ptr() == self._f.data_ptr():
+                self._s = self._s.clone()
+            self._gen.transfer(self._s, z)                     # spectrum *= H, in place (beam2d.py:489)
+            self._f = self._gen.fft2(self._s, inverse=True)    # :490
+            return
         if self._s is None:
             # first step after a coordinate-space update: fused fft2 -> H -> ifft2, the
             # spectrum state (fft2(field)*H) is written as a by-product
@@ -278,6 +306,10 @@ class Beam2D:
     def lens(self, f: float):
         """beam2d.py:508-511."""
         torch = _torch()
+        if self._gen is not None:
+            self._gen.lens(self._f, self.k0, f)
+            self._s = self._gen.fft2(self._f)
+            return
         self._s = torch.empty_like(self._f)
         self._call("lp2d_lens", self._plan.handle, self._f.data_ptr(), self._s.data_ptr(), self._batch(),
                    float(self.k0), float(f), self._stream())
@@ -315,6 +347,15 @@ class Beam2D:
             data = self._s
         else:
             data = self._f
+        if self._gen is not None:
+            for mask in masks:
+                mt, kind, stride = self._mask_to_device(mask)
+                self._gen.mul_mask(data, mt, kind, stride)
+            if spectral:
+                self._f = self._gen.fft2(data, inverse=True)
+            else:
+                self._s = self._gen.fft2(data)
+            return
         other = torch.empty_like(data)
         if not masks:
             masks = [None]
@@ -484,6 +525,8 @@ class Beam2D:
     def iprofile(self):
         """|A|^2 (beam2d.py:717): float32 for complex64, float64 for complex128."""
         torch = _torch()
+        if self._gen is not None:
+            return self._output(self._gen.intensity(self._f))
         out = torch.empty(self._f.shape, dtype=self._rdtype, device=self._tdev)
         self._call("lp2d_intensity", self._plan.handle, self._f.data_ptr(), out.data_ptr(), self._batch(),
                    self._stream())
@@ -503,6 +546,9 @@ class Beam2D:
         torch = _torch()
         if self._batch() != 1:
             raise ValueError("centroid / D4sigma are defined for a single field, as in the reference")
+        if self.npoints % 2:
+            # beam2d.py:680-683: mgrid[-n//2 : n//2] has npoints - 1 points per axis, numpy.average refuses the weights
+            raise TypeError("Axis must be specified when shapes of a and weights differ.")
         out = torch.empty(5, dtype=torch.float64, device=self._tdev)
         self._call("lp2d_moments", _lib.C64 if self.complex_bits == 64 else _lib.C128, self._f.data_ptr(),
                    int(self.npoints), float(self.dL), float(xc), float(yc), out.data_ptr(), self._stream())

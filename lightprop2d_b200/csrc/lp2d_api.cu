@@ -326,7 +326,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     // (3*P*B algorithmic bytes); plain fft2 and the three-stage fresh chain stay on the per-pass kernels
     // and, for the small planes, on more of them (profiles/r1c_size_sweep.log, r1c_group_sweep.log):
     //   complex64 256: + plain fft2; complex64 512 and complex128 256: every step
-    int ops_default = 2;
+    int ops_default = 2;                            // (also complex64 2048: the steps with a state store only)
     if (dtype == LP2D_C64 && n == 256) ops_default = 3;
     if ((dtype == LP2D_C64 && n == 512) || (dtype == LP2D_C128 && n == 256)) ops_default = 7;
     env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : ops_default;

@@ -186,20 +186,61 @@ __global__ void moments_kernel(const cx<T>* __restrict__ f, int n, double dL, do
 }
 
 // SIMT mode projection: coeffs[b][k] = sum_p M[k][p] * field_b[crop(p)]  (no conjugate, beam2d.py:592-600).
-// One CTA per (mode, beam); FP64 accumulation for both field types.
-template <typename T>
-__global__ void modes_project_kernel(const cx<T>* __restrict__ field, const cx<T>* __restrict__ modes,
-                                     cx<T>* __restrict__ coeffs, int n, int nb, int nmodes) {
+// One CTA per (mode, tile of BT beams): a mode sample is loaded ONCE per BT beams (the mode matrix is the big
+// operand: nmodes x nb^2), the BT field samples of the same grid point are coalesced loads of BT planes.
+// FP64 accumulation for both field types.
+template <typename T, int BT>
+__global__ void __launch_bounds__(256) modes_project_kernel(const cx<T>* __restrict__ field, const cx<T>* __restrict__ modes,
+                                                            cx<T>* __restrict__ coeffs, int n, int nb, int nmodes, long long batch) {
     const int k = blockIdx.x;
-    const long long b = blockIdx.y;
+    const long long b0 = (long long)blockIdx.y * BT;
     const int dn = (n - nb) / 2;
+    const long long plane = (long long)n * n;
     const cx<T>* mrow = modes + (long long)k * nb * nb;
-    const cx<T>* f = field + b * (long long)n * n;
-    double ax = 0, ay = 0;
+    const cx<T>* f = field + b0 * plane;
+    const int nbt = (batch - b0 < BT) ? (int)(batch - b0) : BT;
+    double ax[BT], ay[BT];
+#pragma unroll
+    for (int j = 0; j < BT; ++j) ax[j] = ay[j] = 0.0;
     for (int p = threadIdx.x; p < nb * nb; p += blockDim.x) {
         const int r = p / nb, c = p % nb;
-        const cx<T> mv = mrow[p];
-        const cx<T> fv = f[(long long)(r + dn) * n + (c + dn)];
+        const cx<T> mv = __ldcs(&mrow[p]);
+        const long long off = (long long)(r + dn) * n + (c + dn);
+#pragma unroll
+        for (int j = 0; j < BT; ++j) {
+            if (j < nbt) {
+                const cx<T> fv = f[j * plane + off];
+                ax[j] += (double)mv.x * fv.x - (double)mv.y * fv.y;
+                ay[j] += (double)mv.x * fv.y + (double)mv.y * fv.x;
+            }
+        }
+    }
+    __shared__ double sm[2][BT][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < BT; ++j) {
+        const double sx = warp_sum(ax[j]), sy = warp_sum(ay[j]);
+        if (lane == 0) { sm[0][j][w] = sx; sm[1][j][w] = sy; }
+    }
+    __syncthreads();
+    if (threadIdx.x < nbt) {
+        double sx = 0, sy = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { sx += sm[0][threadIdx.x][q]; sy += sm[1][threadIdx.x][q]; }
+        coeffs[(b0 + threadIdx.x) * nmodes + k] = mk<T>((T)sx, (T)sy);
+    }
+}
+
+// Flat form for a strip of the crop (a slab of a grid decomposed over several GPUs): coeffs[k] = sum_{p < K}
+// modes[k * ldm + p] * f[p]; the partial sums of the ranks are added by the caller (one all-reduce).
+template <typename T>
+__global__ void __launch_bounds__(256) modes_project_flat_kernel(const cx<T>* __restrict__ f, const cx<T>* __restrict__ modes,
+                                                                 cx<T>* __restrict__ coeffs, long long K, long long ldm) {
+    const int k = blockIdx.x;
+    const cx<T>* mrow = modes + (long long)k * ldm;
+    double ax = 0, ay = 0;
+    for (long long p = threadIdx.x; p < K; p += blockDim.x) {
+        const cx<T> mv = __ldcs(&mrow[p]);
+        const cx<T> fv = f[p];
         ax += (double)mv.x * fv.x - (double)mv.y * fv.y;
         ay += (double)mv.x * fv.y + (double)mv.y * fv.x;
     }
@@ -211,7 +252,7 @@ __global__ void modes_project_kernel(const cx<T>* __restrict__ field, const cx<T
     if (threadIdx.x == 0) {
         double sx = 0, sy = 0;
         for (int q = 0; q < (int)(blockDim.x >> 5); ++q) { sx += sm[0][q]; sy += sm[1][q]; }
-        coeffs[b * nmodes + k] = mk<T>((T)sx, (T)sy);
+        coeffs[k] = mk<T>((T)sx, (T)sy);
     }
 }
 
@@ -382,12 +423,25 @@ int lp2d_modes_project(int dtype, const void* field, const void* modes, void* co
             if (rc != LP2D_EUNSUPPORTED) return rc;
         }
     }
-    dim3 grid((unsigned)nmodes, (unsigned)batch);
+    constexpr int BT = 8;
+    dim3 grid((unsigned)nmodes, (unsigned)((batch + BT - 1) / BT));
     if (dtype == LP2D_C64)
-        modes_project_kernel<float><<<grid, 256, 0, s>>>((const float2*)field, (const float2*)modes, (float2*)coeffs, n, nb, nmodes);
+        modes_project_kernel<float, BT><<<grid, 256, 0, s>>>((const float2*)field, (const float2*)modes, (float2*)coeffs, n, nb, nmodes, batch);
     else
-        modes_project_kernel<double><<<grid, 256, 0, s>>>((const double2*)field, (const double2*)modes, (double2*)coeffs, n, nb, nmodes);
+        modes_project_kernel<double, BT><<<grid, 256, 0, s>>>((const double2*)field, (const double2*)modes, (double2*)coeffs, n, nb, nmodes, batch);
     return done("modes_project launch");
+}
+
+int lp2d_modes_project_flat(int dtype, const void* flat_field, const void* modes, void* coeffs, long long count, long long ldm,
+                            int nmodes, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || flat_field == nullptr || modes == nullptr || coeffs == nullptr || count < 0 || ldm < count || nmodes <= 0)
+        return set_error(LP2D_EINVAL, "modes_project_flat: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == LP2D_C64)
+        modes_project_flat_kernel<float><<<(unsigned)nmodes, 256, 0, s>>>((const float2*)flat_field, (const float2*)modes, (float2*)coeffs, count, ldm);
+    else
+        modes_project_flat_kernel<double><<<(unsigned)nmodes, 256, 0, s>>>((const double2*)flat_field, (const double2*)modes, (double2*)coeffs, count, ldm);
+    return done("modes_project_flat launch");
 }
 
 int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void* field, int n, int nb, int nmodes,

@@ -7,10 +7,11 @@
 
 namespace lp2d {
 static const P2Ops<float> kP2F32[] = {
-    // 2048 points: a line is two warps (E = 32), 4 lines per CTA; a plane is 32 MB: the ring (2 planes) only partly
-    // stays in L2 (opt-in: LP2D_FUSED_OPS)
-    T3Inst<float, 2048, 32, 4, 2, 3>::entry(),
+    // 2048 points: a line is two warps (E = 32), 4 lines per CTA; a plane is 32 MB and the ring is 2 planes: the
+    // steps with a state store gain 14 % (43.4 vs 50.3 us per beam), plain fft2 and the fresh chain do not
+    // (profiles/r2b_sweep_1024c128_2048c64.log)
     T3Inst<float, 2048, 32, 4, 2>::entry(),
+    T3Inst<float, 2048, 32, 4, 2, 3>::entry(),
     // the first entry of each size is the default (measured best, profiles/r1c_size_sweep.log)
     T3Inst<float, 1024, 32, 8, 2, 3>::entry(),
     T3Inst<float, 1024, 32, 8, 2, 0>::entry(),

@@ -3,10 +3,8 @@
 
 namespace lp2d {
 static const P2Ops<double> kP2F64[] = {
-    // 1024 points: a line is two warps (E = 16), 4 lines per CTA; a plane is 16 MB, the ring holds 2-3 of them
-    T3Inst<double, 1024, 16, 4, 1>::entry(),
-    T3Inst<double, 1024, 16, 2, 3>::entry(),
-    T3Inst<double, 1024, 16, 4, 1, 3>::entry(),
+    // (1024 points, E = 16: 252 registers, one CTA per SM: 24 us per beam against 20 for the per-pass kernels,
+    // profiles/r2b_sweep_1024c128_2048c64.log -- not built)
     T3Inst<double, 512, 16, 4, 3>::entry(),
     T3Inst<double, 512, 16, 8, 2>::entry(),
     T3Inst<double, 256, 16, 8, 3>::entry(),

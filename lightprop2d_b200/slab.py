@@ -69,6 +69,7 @@ class CudaLineBackend:
         self.cdtype = torch.complex64 if complex_bits == 64 else torch.complex128
         self.rdtype = torch.float32 if complex_bits == 64 else torch.float64
         a, b, x2 = kz2_tables(area_size, npoints, wl)
+        self._host_tabs, self._tabs = (a, b, x2), None
         with torch.cuda.device(self.device):
             self.plan = _Plan(npoints, complex_bits, a, b, x2)
             # transposed orientation: line = grid column i, position = grid row j
@@ -97,6 +98,49 @@ class CudaLineBackend:
                        "pass_lines_tiles")
         else:
             _lib.check(self.lib.lp2d_pass_lines(plan.handle, op, x.data_ptr(), out.data_ptr(), *tail), "pass_lines")
+        return out
+
+    def lens(self, x, line0, k0, f):
+        """x *= exp(i (X^2 + Y^2) k0 / (2 f)) in place on the row slab starting at grid row line0 (beam2d.py:508-510)."""
+        if self._tabs is None:
+            a, b, x2 = self._host_tabs
+            self._tabs = self.torch.from_numpy(np.concatenate([a, b, x2])).to(x.device)
+        _lib.check(self.lib.lp2d_pointwise(_lib.C64 if self.bits == 64 else _lib.C128, x.data_ptr(), 1, int(x.shape[0]), self.n,
+                                           int(line0), _lib.PW_LENS, self._tabs.data_ptr(), float(k0), 2.0 * float(f),
+                                           self._stream()), "pointwise")
+
+    def mul_mask(self, x, mask):
+        """x *= mask in place; mask: bool / real / complex array or tensor of x's shape (beam2d.py:338, 369)."""
+        torch = self.torch
+        t = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(mask)))
+        t = t.to(x.device)
+        if t.dtype == torch.bool:
+            t, kind = t.to(torch.uint8), _lib.MASK_U8
+        elif t.is_complex():
+            t, kind = t.to(self.cdtype), _lib.MASK_COMPLEX
+        else:
+            t, kind = t.to(self.rdtype), _lib.MASK_REAL
+        t = t.expand(x.shape).contiguous()
+        _lib.check(self.lib.lp2d_mul_mask(_lib.C64 if self.bits == 64 else _lib.C128, x.data_ptr(), t.data_ptr(), kind, x.numel(), 0, 1,
+                                          self._stream()), "mul_mask")
+
+    def intensity(self, x):
+        out = self.empty(*x.shape, real=True)
+        _lib.check(self.lib.lp2d_intensity_n(_lib.C64 if self.bits == 64 else _lib.C128, x.data_ptr(), out.data_ptr(), x.numel(),
+                                             self._stream()), "intensity_n")
+        return out
+
+    def project(self, flat_field, modes_cols):
+        """partial coeffs[m] = sum_p modes_cols[m][p] * flat_field[p] over this rank's part of the crop: the mode
+        projection kernel on a 1 x K "grid" (tensor cores for complex64 when the shape allows, SIMT otherwise)."""
+        K = int(flat_field.numel())
+        M = int(modes_cols.shape[0])
+        out = self.empty(M)
+        if K == 0:
+            return out.zero_()
+        _lib.check(self.lib.lp2d_modes_project_flat(_lib.C64 if self.bits == 64 else _lib.C128, flat_field.data_ptr(),
+                                                    modes_cols.data_ptr(), out.data_ptr(), K, int(modes_cols.stride(0)), M,
+                                                    self._stream()), "modes_project_flat")
         return out
 
     def pack_transpose(self, x, tile):
@@ -189,10 +233,70 @@ class SlabBeam2D:
         self.field = self.backend.lines(rows, self.r0, inverse=True, intensity=inten, out=self.field)
         return inten
 
+    def _ifft2(self):
+        """field = ifft2(spectrum) from the transposed spectrum slab (no H): the second half of ``propagate``."""
+        cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True)
+        rows = exchange_transpose(cols, self.backend, self.group, tiles=True)
+        self.field = self.backend.lines(rows, self.r0, inverse=True, out=self.field)
+
+    def lens(self, f: float):
+        """beam2d.py:508-511 on this rank's rows: field *= exp(i (X^2 + Y^2) k0 / (2 f)); spectrum = fft2(field)."""
+        self.backend.lens(self.field, self.r0, self.k0, f)
+        self.spectrum_t = self._fft2(self.field)
+
+    def coordinate_filter(self, f_init=None, f_gen=None, fargs=()):
+        """beam2d.py:335-342.  ``f_gen(X, Y_slab, *fargs)`` is evaluated on this rank's rows; ``f_init`` is this rank's
+        ``(N/G, N)`` rows of the mask."""
+        if f_gen is not None:
+            assert callable(f_gen)
+            self.backend.mul_mask(self.field, np.asarray(f_gen(self.X.copy(), self.Y.copy(), *fargs)))
+        if f_init is not None:
+            self.backend.mul_mask(self.field, f_init)
+        self.spectrum_t = self._fft2(self.field)
+
+    def spectral_filter(self, f_init=None, f_gen=None, fargs=()):
+        """beam2d.py:366-373.  This rank holds the spectrum COLUMNS ``r0 .. r1`` transposed: ``f_gen`` is called as
+        ``f_gen(Kx[r0:r1], Ky, *fargs)`` (an ``(N, N/G)`` block of the reference's mask) and transposed; ``f_init``
+        is that block, ``mask[:, r0:r1]``, of the full ``(N, N)`` mask."""
+        Kx = np.fft.fftfreq(self.npoints, d=self.dL)                        # beam2d.py:305
+        if f_gen is not None:
+            assert callable(f_gen)
+            blk = np.asarray(f_gen(Kx[self.r0:self.r1].copy(), Kx.reshape((-1, 1)).copy(), *fargs))
+            self.backend.mul_mask(self.spectrum_t, np.ascontiguousarray(blk.T))
+        if f_init is not None:
+            blk = f_init.T if isinstance(f_init, np.ndarray) else f_init.transpose(0, 1)
+            self.backend.mul_mask(self.spectrum_t, blk)
+        self._ifft2()
+
     @property
     def iprofile(self):
         """This rank's rows of ``abs(field)**2`` (beam2d.py:717)."""
-        return self.field.real ** 2 + self.field.imag ** 2
+        return self.backend.intensity(self.field)
+
+    def deconstruct_by_modes(self, modes_list):
+        """beam2d.py:592-600 ('scalar') on the decomposed grid: every rank projects
+        the part of the centre ``nb x nb`` crop that lies in its rows onto the matching columns of the mode
+        matrix, the partial coefficient vectors are summed with ONE all-reduce (``nmodes`` complex numbers)."""
+        import torch
+        import torch.distributed as dist
+        dev = self.field.device
+        M = modes_list if isinstance(modes_list, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(modes_list)))
+        if M.dim() != 2:
+            M = M.reshape(M.shape[0], -1)
+        nb = int(np.sqrt(M.shape[1]))
+        dN = (self.npoints - nb) // 2                                        # beam2d.py:593
+        lo, hi = max(self.r0, dN), min(self.r1, dN + nb)                     # grid rows of the crop owned here
+        if hi > lo:
+            strip = self.field[lo - self.r0:hi - self.r0, dN:dN + nb].contiguous().reshape(-1)
+            cols = M[:, (lo - dN) * nb:(hi - dN) * nb].to(dev).to(self.field.dtype)
+            part = self.backend.project(strip, cols)
+        else:
+            part = self.backend.empty(int(M.shape[0])).zero_()
+        if self.world > 1:
+            buf = torch.view_as_real(part)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        self.modes_coeffs = part
+        return part
 
     def gather_field(self):
         """The full N x N field on every rank (debug / small grids)."""

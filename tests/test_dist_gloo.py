@@ -110,6 +110,21 @@ class _NumpyLineBackend:
         rows, ld = x.shape
         return x.reshape(rows, ld // tile, tile).permute(1, 2, 0).contiguous()
 
+    def lens(self, x, line0, k0, f):
+        X = self.g["X"]
+        ph = (X[None, :] ** 2 + X[line0:line0 + x.shape[0], None] ** 2) * k0 / (2 * f)      # beam2d.py:508
+        x.copy_(torch.from_numpy((x.numpy() * (np.cos(ph) + 1j * np.sin(ph))).astype(self.npc)))
+
+    def mul_mask(self, x, mask):
+        m = mask.numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)
+        x.copy_(torch.from_numpy((x.numpy() * m).astype(self.npc)))
+
+    def intensity(self, x):
+        return torch.from_numpy(np.abs(x.numpy()) ** 2)
+
+    def project(self, flat_field, modes_cols):
+        return torch.from_numpy((modes_cols.numpy() @ flat_field.numpy()).astype(self.npc))
+
 
 def _slab_worker(rank, world, port, n, bits, q, reads_tiles=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -128,8 +143,18 @@ def _slab_worker(rank, world, port, n, bits, q, reads_tiles=False):
         b.propagate(z2)
         fld = b.gather_field().numpy()
         spec = b.gather_spectrum().numpy()
+        # lens, filters and the K-split mode projection (partial sums + one all-reduce) on the decomposed grid
+        from lightprop2d_b200 import profiles as prof
+        b.lens(0.01)
+        mask = np.random.default_rng(6).standard_normal((n, n)) + 0.5
+        b.coordinate_filter(f_gen=prof.round_hole, fargs=(area / 3,), f_init=mask[r0:r1])
+        b.spectral_filter(f_gen=prof.rectangle_hole, fargs=(4000., 2500.), f_init=mask[:, r0:r1])
+        fld2 = b.gather_field().numpy()
+        nb = n // 2
+        modes = np.random.default_rng(7).standard_normal((3, nb * nb)) + 1j * np.random.default_rng(8).standard_normal((3, nb * nb))
+        coeffs = b.deconstruct_by_modes(modes.astype(full.dtype)).numpy()
         if rank == 0:
-            q.put((full, spec0, fld, spec, inten.numpy(), b.z))
+            q.put((full, spec0, fld, spec, inten.numpy(), b.z, fld2, mask, modes, coeffs))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -149,7 +174,7 @@ def test_two_rank_slab_matches_oracle(reads_tiles):
     procs = [ctx.Process(target=_slab_worker, args=(r, world, port, n, bits, q, reads_tiles)) for r in range(world)]
     for p in procs:
         p.start()
-    full, spec0, fld, spec, inten0, z = q.get(timeout=180)
+    full, spec0, fld, spec, inten0, z, fld2, mask, modes, coeffs = q.get(timeout=180)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -163,6 +188,13 @@ def test_two_rank_slab_matches_oracle(reads_tiles):
     assert abs(z - o.z) < 1e-15
     assert np.linalg.norm(fld - o.field) <= 1e-12 * np.linalg.norm(o.field)
     assert np.linalg.norm(spec - o.spectrum) <= 1e-12 * np.linalg.norm(o.spectrum)
+    from lightprop2d_b200 import profiles as prof
+    o.lens(0.01)
+    o.coordinate_filter(f_gen=prof.round_hole, fargs=(area / 3,), f_init=mask)
+    o.spectral_filter(f_gen=prof.rectangle_hole, fargs=(4000., 2500.), f_init=mask)
+    assert np.linalg.norm(fld2 - o.field) <= 1e-12 * np.linalg.norm(o.field)
+    want = o.deconstruct_by_modes(modes.astype(full.dtype))
+    assert np.linalg.norm(coeffs - want) <= 1e-11 * np.linalg.norm(want)
 
 
 def test_slab_rows_validation():

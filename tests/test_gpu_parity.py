@@ -97,8 +97,17 @@ def test_golden_expand_coarse(bits):
     assert rel_l2(b.field, g["field_c"]) <= TOL[bits]
     assert rel_l2(b.spectrum, g["spectrum_c"]) <= TOL[bits]
     b.propagate(30 * um)
-    with pytest.raises(NotImplementedError):      # 82 points: not a power of two -> loud, no fallback
-        b.expand(520 * um)
+    b.expand(520 * um)                            # 64 -> 82 points: not a power of two (Bluestein engine)
+    assert b.npoints == int(g["n_e2"]) and np.array_equal(b.X, g["X_e2"])
+    assert rel_l2(b.field, g["field_e2"]) <= TOL[bits]
+    b.propagate(10 * um)
+    # odd npoints -> even npoints: the difference is odd, the reference's padded array (n + 2*(d//2)) and its grids
+    # disagree (latent bug, beam2d.py:385-401); refused loudly, and a refused call leaves the beam as it was
+    c = Beam2D(70 * um, 7, 632 * nm, init_field_gen=lp.plane_wave, complex_bits=bits)
+    with pytest.raises(NotImplementedError):
+        c.expand(100 * um)
+    assert (c.npoints, c.area_size) == (7, 70 * um)
+    c.propagate(10 * um)
 
 
 @pytest.mark.parametrize("bits", BITS)
@@ -287,6 +296,70 @@ def test_oracle_large_sizes(bits, n):
 
 
 @pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("n", [7, 30, 48, 82, 100, 130, 250, 1000])
+def test_arbitrary_npoints_vs_oracle(bits, n):
+    """The reference takes ANY npoints (beam2d.py:299-308; odd n: X = arange(-n//2, n//2) is not centred).  Here such
+    grids run through Bluestein on the power-of-two kernels: fft2, lens, propagate, both filters, observables."""
+    rng = np.random.default_rng(300 + n)
+    f0 = (rng.uniform(size=(n, n)) * np.exp(2j * np.pi * rng.uniform(size=(n, n)))).astype(CT[bits])
+    area, wl = 4e-1 * n / 1024, 532e-7
+    b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    assert np.array_equal(b.X, o.X) and np.array_equal(b.Kx, o.Kx)
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    for f, z in ((0.1, 0.02), (-0.3, 10.0)):
+        b.lens(f); o.lens(f)
+        b.propagate(z); o.propagate(z)
+        assert rel_l2(b.field, o.field) <= TOL[bits], (f, z)
+        assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits], (f, z)
+        assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits], (f, z)
+    mask = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    b.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,), f_init=mask.astype(CT[bits]))
+    o.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,), f_init=mask.astype(CT[bits]))
+    assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+    b.spectral_filter(f_init=np.abs(mask)); o.spectral_filter(f_init=np.abs(mask))
+    assert rel_l2(b.field, o.field) <= TOL[bits]
+    if n % 2 == 0:
+        assert np.allclose(b.centroid[:2], o.centroid[:2], rtol=1e-4 if bits == 64 else 1e-10, atol=1e-12)
+    else:       # the reference's mgrid[-n//2 : n//2] has n - 1 points for odd n: numpy refuses the weights
+        with pytest.raises(TypeError):
+            o.centroid
+        with pytest.raises(TypeError):
+            b.centroid
+    # batched: (3, n, n) equals the per-beam results
+    f3 = np.stack([f0, 1j * f0, f0[::-1]]).astype(CT[bits])
+    b3 = Beam2D(area, n, wl, init_field=f3.copy(), complex_bits=bits)
+    b3.propagate(0.05)
+    o1 = orc.OracleBeam(area, n, wl, init_field=f3[2].copy(), complex_bits=bits)
+    o1.propagate(0.05)
+    assert rel_l2(b3.field[2], o1.field) <= TOL[bits]
+
+
+def test_long_line_grid_complex128_8192():
+    """The reference's own timing script runs 8192^2 complex128 (tests/gaussbeam_performance.py:16-30): above the 2-D
+    plans, served by the long-line (cluster) kernels with a tiled transpose.  fft2 against numpy on the host, then
+    lens + propagate through size-independent properties."""
+    n, area, wl = 8192, 4e-1, 532e-7
+    x = np.arange(-n // 2, n // 2) * (area / n)
+    rng = np.random.default_rng(8)
+    f0 = lp.rectangle_hole(x, x.reshape(-1, 1), 2e-1, 1e-1) * np.exp(2j * np.pi * rng.uniform(size=(n, n)))
+    b = Beam2D(area, n, wl, init_field=f0, complex_bits=128, use_gpu=True, numpy_output=False)
+    ref = np.fft.fft2(f0)
+    got = b.spectrum.cpu().numpy()
+    assert rel_l2(got, ref) <= TOL[128]
+    del got, ref
+    e0 = float(b.iprofile.sum())
+    f_in = b.field.clone()
+    b.lens(0.3)
+    b.propagate(0.7)
+    assert abs(float(b.iprofile.sum()) - e0) <= 1e-10 * e0
+    b.propagate(-0.7)
+    b.lens(-0.3)
+    d = (b.field - f_in).abs().pow(2).sum().sqrt() / f_in.abs().pow(2).sum().sqrt()
+    assert float(d) <= 1e-11
+
+
+@pytest.mark.parametrize("bits", BITS)
 def test_evanescent_region_passes_unattenuated(bits):
     """k0 < |K| somewhere: sqrt gives NaN -> 0 -> H = 1 (beam2d.py:307-308), reproduced."""
     n, area, wl = 64, 0.05, 2e-3
@@ -302,8 +375,8 @@ def test_evanescent_region_passes_unattenuated(bits):
 def test_constructor_errors_and_dtypes():
     with pytest.raises(ValueError, match="Init field data is None"):
         Beam2D(200 * um, 64, 632 * nm)
-    with pytest.raises(NotImplementedError):
-        Beam2D(200 * um, 48, 632 * nm, init_field_gen=lp.plane_wave)
+    with pytest.raises(NotImplementedError):      # Bluestein size 16384 is above the largest 2-D plan
+        Beam2D(200 * um, 5000, 632 * nm, init_field_gen=lp.plane_wave, complex_bits=64)
     with pytest.raises(ValueError):
         Beam2D(200 * um, 64, 632 * nm, init_field=np.ones((32, 32)))
     with pytest.raises(ValueError, match="Unknown type"):
@@ -444,6 +517,22 @@ def test_slab_single_rank_matches_oracle(bits, n, tol):
     o.propagate(-40 * lp.um)
     assert rel_l2(b.field.cpu().numpy(), o.field) <= tol[bits]
     assert rel_l2(b.gather_spectrum().cpu().numpy(), o.spectrum) <= tol[bits]
+    # lens, both filters, iprofile and the mode projection on the decomposed grid (beam2d.py:508-511, 335-373, 592-600)
+    b.lens(0.3); o.lens(0.3)
+    assert rel_l2(b.gather_spectrum().cpu().numpy(), o.spectrum) <= tol[bits]
+    mask = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    b.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,), f_init=mask.astype(ct))
+    o.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,), f_init=mask.astype(ct))
+    assert rel_l2(b.gather_spectrum().cpu().numpy(), o.spectrum) <= tol[bits]
+    b.spectral_filter(f_gen=lp.rectangle_hole, fargs=(4000., 2500.), f_init=np.abs(mask))
+    o.spectral_filter(f_gen=lp.rectangle_hole, fargs=(4000., 2500.), f_init=np.abs(mask))
+    assert rel_l2(b.field.cpu().numpy(), o.field) <= tol[bits]
+    b.propagate(25 * lp.um); o.propagate(25 * lp.um)
+    assert rel_l2(b.iprofile.cpu().numpy(), o.iprofile) <= tol[bits]
+    nb, M = n // 2, 5
+    modes = ((rng.standard_normal((M, nb * nb)) + 1j * rng.standard_normal((M, nb * nb))) / nb).astype(ct)
+    got = b.deconstruct_by_modes(modes).cpu().numpy()
+    assert rel_l2(got, o.deconstruct_by_modes(modes)) <= 10 * tol[bits]
 
 
 @pytest.mark.gpu
