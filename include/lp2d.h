@@ -231,6 +231,20 @@ LP2D_API int lp2d_bluestein_post(int dtype, const void* in, void* out, int n, in
                         void* stream);
 LP2D_API int lp2d_bluestein_filter(int dtype, void* out, int n, int m, int inverse, void* stream);
 
+/* Dense solve A X = B on the device for the mode decomposition (beam2d.py:601-603 through the normal equations,
+ * :649-650): one m x m system, nrhs right-hand sides, complex128 row-major, LU with partial pivoting in one CTA.
+ * A is destroyed, B receives X.  dev_info (device int): 0, or k + 1 when pivot k is exactly zero (singular). */
+LP2D_API int lp2d_solve(void* A, void* B, int m, int nrhs, int* dev_info, void* stream);
+
+/* Tensor-product linear interpolation, the evaluation behind the reference's interp2d (crop, lens_image:
+ * beam2d.py:427-434, 527-535): out[b][r][c] = sum_{i,j in {0,1}} in[b][iy[r] + j][ix[c] + i] * wx[i][c] * wy[j][r].
+ * `in` planes are in_plane samples apart with row stride ld_in (a window of a larger plane is fine); ix / iy (n_out
+ * ints) are the lower knot of the interval, wx / wy (2 x n_out doubles) the two weights -- computed on the host from
+ * the coordinate vectors with the reference's expressions (2 n_out numbers), see beam2d.py here. */
+LP2D_API int lp2d_resample(int dtype, const void* in, long long in_plane, int ld_in, void* out, int n_out,
+                  const int* dev_ix, const double* dev_wx, const int* dev_iy, const double* dev_wy,
+                  long long batch, void* stream);
+
 /* Which kernel family serves the steps of this plan that read and write state (propagate, lens,
  * mask + fft2): 0 = one kernel per pass (row pass, column pass), 1 = the fused step kernel (one
  * launch per step, row <-> column intermediate in an L2-resident ring).  `name` (may be NULL)

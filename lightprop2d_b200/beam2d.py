@@ -427,10 +427,56 @@ class Beam2D:
         self._f = out
         self._s = None
 
+    @staticmethod
+    def _linear_knots(xs, xq):
+        """Interval index and the two weights of the degree-1 spline FITPACK evaluates for the reference's ``interp2d``
+        (kind='linear'): arguments outside [xs[0], xs[-1]] are clamped (fpbisp), interval l with xs[l] <= x < xs[l+1]
+        (the last one closed), weights (xs[l+1] - x) / h and (x - xs[l]) / h.  2 n numbers, built on the host."""
+        xs = np.asarray(xs, dtype=np.float64)
+        x = np.clip(np.asarray(xq, dtype=np.float64), xs[0], xs[-1])
+        l = np.clip(np.searchsorted(xs, x, side="right") - 1, 0, len(xs) - 2)
+        h = xs[l + 1] - xs[l]
+        w = np.stack([(xs[l + 1] - x) / h, (x - xs[l]) / h])
+        return l.astype(np.int32), np.ascontiguousarray(w)
+
+    def _resample(self, src, src_plane, ld_in, n_out, xs, xq):
+        """Bilinear resampling of (a window of) ``src`` onto the mesh xq x xq, on the device (``lp2d_resample``)."""
+        torch = _torch()
+        idx, w = self._linear_knots(xs, xq)
+        d_idx = torch.from_numpy(idx).to(self._tdev)
+        d_w = torch.from_numpy(w).to(self._tdev)
+        out = torch.empty(*self._f.shape[:-2], n_out, n_out, dtype=self._cdtype, device=self._tdev)
+        self._call("lp2d_resample", _lib.C64 if self.complex_bits == 64 else _lib.C128, src.data_ptr(), int(src_plane), int(ld_in),
+                   out.data_ptr(), int(n_out), d_idx.data_ptr(), d_w.data_ptr(), d_idx.data_ptr(), d_w.data_ptr(), self._batch(),
+                   self._stream())
+        return out
+
     def crop(self, area_size: float, npoints: int = 0):
-        raise NotImplementedError(
-            "crop resamples through scipy.interpolate.interp2d on the host in the reference "
-            "(beam2d.py:419-435) and has no working oracle on SciPy >= 1.14; out of scope")
+        """beam2d.py:419-435: keep the window ``|X| < area_size / 2`` of the field and resample it (linear
+        ``interp2d`` in the reference: a tensor-product linear spline, evaluated here on the device) onto the new
+        ``npoints`` grid of the new area.  The reference itself cannot run this on SciPy >= 1.14 (``interp2d`` was
+        removed); parity is defined against ``RectBivariateSpline(kx=1, ky=1)``, SciPy's documented replacement."""
+        old_X = self.X[np.abs(self.X) < area_size / 2]
+        Nc = self.npoints // 2
+        n = len(old_X) // 2
+        if n < 1:
+            raise ValueError("crop: the new area holds fewer than two grid points")
+        old_X = self.X[Nc - n:Nc + n].copy()
+        old_n = self.npoints
+        saved = (self.npoints, self.area_size)
+        if npoints:
+            self.npoints = npoints
+        self.area_size = area_size
+        try:
+            self._construct_grids()
+            self._new_plan()
+        except Exception:
+            self.npoints, self.area_size = saved
+            self._construct_grids()
+            raise
+        win = self._f.reshape(-1, old_n, old_n)[:, Nc - n:, Nc - n:]          # view: window origin, full row stride
+        self._f = self._resample(win, old_n * old_n, old_n, self.npoints, old_X, self.X)
+        self._s = None
 
     def coarse(self, mean_order: int = 1):
         """beam2d.py:454-460: npoints //= m, block mean of the field, fft2."""
@@ -455,9 +501,25 @@ class Beam2D:
         self._s = None
 
     def lens_image(self, f: float, l1: float, l2: float):
-        raise NotImplementedError(
-            "lens_image resamples through scipy.interpolate.interp2d on the host in the reference "
-            "(beam2d.py:525-536) and has no working oracle on SciPy >= 1.14; out of scope")
+        """beam2d.py:525-536: image through a lens between conjugated planes.  Reference quirks kept: ``X`` (and,
+        through the view, ``Y``) is scaled IN PLACE by ``-l1 / l2`` and stays scaled; ``interp2d.__call__`` sorts its
+        arguments, so the mesh is ascending whatever the sign of the scale; the phase uses the grid before the
+        scaling.  Resampling on the device, parity against ``RectBivariateSpline(kx=1, ky=1)`` as for ``crop``."""
+        torch = _torch()
+        scale_factor = - l1 / l2
+        X = self.X
+        xs = X.copy()
+        phase = - (self.X ** 2 + self.Y ** 2) * self.k0 * (l1 + l2) / 2 / l2 ** 2
+        X *= scale_factor                                     # in place: self.X and self.Y change (beam2d.py:531)
+        n = self.npoints
+        res = self._resample(self._f, n * n, n, n, xs, np.sort(X))
+        mask = scale_factor * (np.cos(phase) + 1j * np.sin(phase))
+        mt, kind, stride = self._mask_to_device(mask)
+        self._f = res
+        self._new_plan()                                      # the grid changed: lens() after this uses the scaled X
+        self._call("lp2d_mul_mask", _lib.C64 if self.complex_bits == 64 else _lib.C128, self._f.data_ptr(), mt.data_ptr(), kind,
+                   n * n, stride, self._batch(), self._stream())
+        self._s = None
 
     # -------------------------------------------------------------------- modes
     def _modes_to_device(self, modes_list):
@@ -473,15 +535,56 @@ class Beam2D:
     def deconstruct_by_modes(self, modes_list, mode: str = 'scalar'):
         """beam2d.py:592-604, 'scalar' branch on the GPU: coeffs = M @ vec(centre crop), no conjugate."""
         torch = _torch()
+        if mode == 'lstsq':
+            return self._deconstruct_lstsq(modes_list)
         if mode != 'scalar':
-            raise NotImplementedError("deconstruct_by_modes(mode='lstsq') is not on the CUDA path (SURVEY.md §8f rank 3)")
+            return getattr(self, "modes_coeffs", None)        # the reference falls through both branches
+        self.modes_coeffs = self._expose(self._project_dev(modes_list))
+        return self.modes_coeffs
+
+    def _project_dev(self, modes_list):
+        torch = _torch()
         M = self._modes_to_device(modes_list)
         nb = int(np.sqrt(M.shape[1]))
         out = torch.empty(*self._f.shape[:-2], M.shape[0], dtype=self._cdtype, device=self._tdev)
         self._call("lp2d_modes_project", _lib.C64 if self.complex_bits == 64 else _lib.C128, self._f.data_ptr(),
                    M.data_ptr(), out.data_ptr(), int(self.npoints), nb, int(M.shape[0]), self._batch(),
                    self._stream())
-        self.modes_coeffs = self._expose(out)
+        return out
+
+    def _project128(self, fields128, M128, n, nb):
+        torch = _torch()
+        batch = fields128.numel() // (n * n)
+        out = torch.empty(batch, M128.shape[0], dtype=torch.complex128, device=self._tdev)
+        self._call("lp2d_modes_project", _lib.C128, fields128.data_ptr(), M128.data_ptr(), out.data_ptr(), int(n), int(nb),
+                   int(M128.shape[0]), batch, self._stream())
+        return out
+
+    def _solve(self, A, B):
+        """A X = B on the device (``lp2d_solve``: LU with partial pivoting, complex128); returns X (M, nrhs)."""
+        torch = _torch()
+        A = A.to(torch.complex128).contiguous().clone()
+        B = B.to(torch.complex128).contiguous().clone()
+        info = torch.zeros(1, dtype=torch.int32, device=self._tdev)
+        self._call("lp2d_solve", A.data_ptr(), B.data_ptr(), int(A.shape[0]), int(B.shape[1]), info.data_ptr(), self._stream())
+        return B
+
+    def _deconstruct_lstsq(self, modes_list):
+        """beam2d.py:601-603: ``lstsq(modes_matrix.T, vec(crop), rcond=-1)[0]``, here through the normal equations on
+        the device in complex128 whatever the field type: G = conj(M) M^T and conj(M) f come from the mode projection
+        kernel (the rows of conj(M) are projected like a batch of fields), the M x M solve is ``lp2d_solve``.  Equal to
+        the reference's SVD solution when the modes are linearly independent (cond(M)^2 eps accuracy); a rank-deficient
+        basis, where numpy returns the minimum-norm solution, is reported by a ValueError."""
+        torch = _torch()
+        M = self._modes_to_device(modes_list).to(torch.complex128)
+        nm, nb = int(M.shape[0]), int(np.sqrt(M.shape[1]))
+        G = self._project128(M.conj().resolve_conj().contiguous(), M, nb, nb)             # G[l][k] = sum conj(M_l) M_k
+        rhs = self._project128(self._f.to(torch.complex128).conj().resolve_conj().contiguous(), M, self.npoints, nb).conj()
+        X = self._solve(G, rhs.reshape(-1, nm).transpose(0, 1))
+        sol = X.transpose(0, 1).reshape(*self._f.shape[:-2], nm).to(self._cdtype)
+        if not bool(torch.isfinite(torch.view_as_real(sol)).all()):
+            raise ValueError("deconstruct_by_modes(mode='lstsq'): the mode basis is rank deficient")
+        self.modes_coeffs = self._expose(sol.contiguous())
         return self.modes_coeffs
 
     def fast_deconstruct_by_modes(self, modes_matrix_t, modes_matrix_dot_t):
@@ -489,14 +592,16 @@ class Beam2D:
         flattened modes, ``MtM`` the (M, M) system matrix.  The projection ``Mt . f`` (M x K, the expensive
         part) runs on the GPU (tensor cores for complex64); the M x M least-squares solve is the reference's own
         ``numpy.linalg.lstsq`` call on the host (tiny, LAPACK)."""
+        torch = _torch()
+        keep = self.numpy_output, self.use_gpu
         proj = self.deconstruct_by_modes(modes_matrix_t, mode='scalar')
-        proj = self._np(proj) if not isinstance(proj, np.ndarray) else proj
-        mtm = np.asarray(self._np(modes_matrix_dot_t) if not isinstance(modes_matrix_dot_t, np.ndarray) else modes_matrix_dot_t)
-        if proj.ndim == 1:
-            sol = np.linalg.lstsq(mtm, proj, rcond=None)[0]
-        else:   # a batch of beams: one right-hand side per beam
-            sol = np.linalg.lstsq(mtm, proj.reshape(-1, proj.shape[-1]).T, rcond=None)[0].T.reshape(proj.shape)
-        self.modes_coeffs = sol.astype(self.complex) if sol.dtype != self.complex else sol
+        proj = proj if isinstance(proj, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(proj)).to(self._tdev)
+        mtm = modes_matrix_dot_t
+        mtm = (mtm if isinstance(mtm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(mtm)))).to(self._tdev)
+        nm = int(proj.shape[-1])
+        X = self._solve(mtm, proj.reshape(-1, nm).transpose(0, 1))           # one right-hand side per beam
+        sol = X.transpose(0, 1).reshape(proj.shape).to(self._cdtype).contiguous()
+        self.modes_coeffs = self._expose(sol)
         return self.modes_coeffs
 
     def construct_by_modes(self, modes_list, modes_coeffs):

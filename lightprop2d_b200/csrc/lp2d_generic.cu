@@ -239,3 +239,160 @@ int lp2d_bluestein_filter(int dtype, void* out, int n, int m, int inverse, void*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small dense solve and bilinear resampling (the "next" rows of SURVEY.md section 8f).
+namespace lp2d {
+
+// A X = B for one M x M complex128 system with nrhs right-hand sides, LU with partial pivoting, ONE CTA (the systems
+// of the mode decomposition are a few hundred unknowns: beam2d.py:601-603, 649-650).  A and B are overwritten
+// (B by the solution).  info[0] = 0, or k + 1 when the k-th pivot is exactly zero.
+__global__ void __launch_bounds__(1024) lu_solve_kernel(double2* __restrict__ A, double2* __restrict__ B, int M, int nrhs, int* info) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    __shared__ double2 s_inv;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) info[0] = 0;
+    for (int k = 0; k < M; ++k) {
+        // pivot search in column k
+        double best = -1.0; int bi = k;
+        for (int r = k + tid; r < M; r += nt) {
+            const double2 v = A[(long long)r * M + k];
+            const double a = fabs(v.x) + fabs(v.y);              // LAPACK's cabs1
+            if (a > best) { best = a; bi = r; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double b = s_val[0]; int i = s_idx[0];
+            for (int w = 1; w < (nt + 31) / 32; ++w)
+                if (s_val[w] > b || (s_val[w] == b && s_idx[w] < i)) { b = s_val[w]; i = s_idx[w]; }
+            s_piv = i;
+            if (b == 0.0 && info[0] == 0) info[0] = k + 1;
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p != k) {                                               // swap rows k and p (columns k.., and B)
+            for (int c = k + tid; c < M; c += nt) {
+                const double2 t = A[(long long)k * M + c]; A[(long long)k * M + c] = A[(long long)p * M + c]; A[(long long)p * M + c] = t;
+            }
+            for (int c = tid; c < nrhs; c += nt) {
+                const double2 t = B[(long long)k * nrhs + c]; B[(long long)k * nrhs + c] = B[(long long)p * nrhs + c]; B[(long long)p * nrhs + c] = t;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double2 d = A[(long long)k * M + k];
+            const double den = d.x * d.x + d.y * d.y;
+            s_inv = den > 0.0 ? make_double2(d.x / den, -d.y / den) : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        const double2 inv = s_inv;
+        // multipliers, then the rank-1 update of the trailing block and of B
+        for (int r = k + 1 + tid; r < M; r += nt) A[(long long)r * M + k] = dmul(A[(long long)r * M + k], inv);
+        __syncthreads();
+        const int rem = M - k - 1;
+        for (long long e = tid; e < (long long)rem * (rem + nrhs); e += nt) {
+            const int r = k + 1 + (int)(e / (rem + nrhs));
+            const int c = (int)(e % (rem + nrhs));
+            const double2 l = A[(long long)r * M + k];
+            if (c < rem) {
+                const double2 u = A[(long long)k * M + k + 1 + c];
+                double2& t = A[(long long)r * M + k + 1 + c];
+                const double2 pr = dmul(l, u);
+                t.x -= pr.x; t.y -= pr.y;
+            } else {
+                const double2 u = B[(long long)k * nrhs + (c - rem)];
+                double2& t = B[(long long)r * nrhs + (c - rem)];
+                const double2 pr = dmul(l, u);
+                t.x -= pr.x; t.y -= pr.y;
+            }
+        }
+        __syncthreads();
+    }
+    // back substitution: U X = B
+    for (int k = M - 1; k >= 0; --k) {
+        if (tid == 0) {
+            const double2 d = A[(long long)k * M + k];
+            const double den = d.x * d.x + d.y * d.y;
+            s_inv = den > 0.0 ? make_double2(d.x / den, -d.y / den) : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        const double2 inv = s_inv;
+        for (int c = tid; c < nrhs; c += nt) B[(long long)k * nrhs + c] = dmul(B[(long long)k * nrhs + c], inv);
+        __syncthreads();
+        for (long long e = tid; e < (long long)k * nrhs; e += nt) {
+            const int r = (int)(e / nrhs), c = (int)(e % nrhs);
+            const double2 pr = dmul(A[(long long)r * M + k], B[(long long)k * nrhs + c]);
+            double2& t = B[(long long)r * nrhs + c];
+            t.x -= pr.x; t.y -= pr.y;
+        }
+        __syncthreads();
+    }
+}
+
+// out[b][r][c] = sum_{i, j in {0, 1}} in[b][iy[r] + i][ix[c] + j] * wy[i][r] * wx[j][c]: the tensor-product linear
+// spline FITPACK evaluates for the reference's interp2d (beam2d.py:427-434, 527-535), weights and knot intervals from
+// the host (they depend on 2 n numbers only), summed in FITPACK's order ((c * hx) * hy, i outer, j inner) in FP64.
+template <typename T>
+__global__ void resample_kernel(const cx<T>* __restrict__ in, long long in_plane, int ld_in, cx<T>* __restrict__ out, int n_out,
+                                const int* __restrict__ ix, const double* __restrict__ wx, const int* __restrict__ iy,
+                                const double* __restrict__ wy, long long batch) {
+    const long long plane = (long long)n_out * n_out;
+    const long long total = batch * plane;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / plane, q = e - b * plane;
+        const int r = (int)(q / n_out), c = (int)(q - (long long)r * n_out);
+        const cx<T>* src = in + b * in_plane + (long long)iy[r] * ld_in + ix[c];
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                  // x interval (FITPACK's first index = our columns)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {              // y interval
+                const cx<T> v = src[(long long)j * ld_in + i];
+                const double hx = wx[i * n_out + c], hy = wy[j * n_out + r];
+                sx += ((double)v.x * hx) * hy;
+                sy += ((double)v.y * hx) * hy;
+            }
+        }
+        out[e] = mk<T>((T)sx, (T)sy);
+    }
+}
+}  // namespace lp2d
+
+extern "C" {
+
+int lp2d_solve(void* A, void* B, int m, int nrhs, int* dev_info, void* stream) {
+    if (A == nullptr || B == nullptr || dev_info == nullptr || m < 1 || nrhs < 1) return set_error(LP2D_EINVAL, "solve: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    lu_solve_kernel<<<1, 1024, 0, s>>>(static_cast<double2*>(A), static_cast<double2*>(B), m, nrhs, dev_info);
+    LP2D_LAUNCH_CHECK("solve launch");
+    return LP2D_OK;
+}
+
+int lp2d_resample(int dtype, const void* in, long long in_plane, int ld_in, void* out, int n_out, const int* dev_ix,
+                  const double* dev_wx, const int* dev_iy, const double* dev_wy, long long batch, void* stream) {
+    if (in == nullptr || out == nullptr || dev_ix == nullptr || dev_wx == nullptr || dev_iy == nullptr || dev_wy == nullptr || n_out < 1 ||
+        ld_in < 2 || batch < 0)
+        return set_error(LP2D_EINVAL, "resample: bad arguments");
+    if (dtype != LP2D_C64 && dtype != LP2D_C128) return set_error(LP2D_EINVAL, "resample: bad dtype");
+    const long long total = batch * (long long)n_out * n_out;
+    if (total == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == LP2D_C64)
+        resample_kernel<float><<<grid_for(total), 256, 0, s>>>(static_cast<const float2*>(in), in_plane, ld_in, static_cast<float2*>(out), n_out,
+                                                                dev_ix, dev_wx, dev_iy, dev_wy, batch);
+    else
+        resample_kernel<double><<<grid_for(total), 256, 0, s>>>(static_cast<const double2*>(in), in_plane, ld_in, static_cast<double2*>(out), n_out,
+                                                                 dev_ix, dev_wx, dev_iy, dev_wy, batch);
+    LP2D_LAUNCH_CHECK("resample launch");
+    return LP2D_OK;
+}
+
+}  // extern "C"

@@ -14,6 +14,13 @@ reference from /root/reference through ``oracle/ref_shim.py``) and committed und
 (grids) / to <= 4 ulp-level tolerance (FFT results on the same numpy build are
 bit-identical; the tolerance only guards against a different numpy on the GPU box).
 
+PARITY UNPINNED for ``crop`` and ``lens_image`` only: the reference resamples with
+``scipy.interpolate.interp2d`` (beam2d.py:427-434, 527-535), which SciPy removed in 1.14 (the reference
+raises NotImplementedError here, 1.18).  Those two functions are restated with SciPy's documented
+replacement, ``RectBivariateSpline(x, y, z.T, kx=1, ky=1)`` (same FITPACK routines: regrid + bispev), plus
+the two behaviours of the removed class that matter: ``__call__`` sorted its arguments, and arguments
+outside the data range are clamped.
+
 The third-party arithmetic on the path: numpy (unpinned by the
 reference; 2.3.5 here) ``numpy.fft.fft2/ifft2`` (pocketfft, forward unscaled,
 inverse scaled by 1/N^2), ``numpy.fft.fftfreq`` (``k * (1.0/(n*d))`` with integer
@@ -206,6 +213,44 @@ def modes_fast_lstsq(field: np.ndarray, modes_matrix_t: np.ndarray, modes_matrix
     return np.linalg.lstsq(np.asarray(modes_matrix_dot_t), modes_matrix_t.dot(flat), rcond=None)[0]
 
 
+def modes_lstsq(field: np.ndarray, modes: np.ndarray) -> np.ndarray:
+    """deconstruct_by_modes(mode='lstsq'), beam2d.py:601-603: lstsq(modes_matrix.T, vec(centre crop), rcond=-1)[0]."""
+    modes = np.vstack(np.asarray(modes))
+    n = field.shape[-1]
+    Nb = int(np.sqrt(modes.shape[1]))
+    dN = (n - Nb) // 2
+    flat = field[dN:n - dN, dN:n - dN].flatten()
+    return np.linalg.lstsq(modes.T, flat, rcond=-1)[0]
+
+
+def _interp2d_linear(xs, z, xq):
+    """What ``interp2d(xs, xs, z)(xq, xq)`` returned (kind='linear'): SciPy's replacement recipe."""
+    from scipy.interpolate import RectBivariateSpline
+    xq = np.sort(np.asarray(xq, dtype=np.float64))                  # interp2d.__call__ sorted x and y
+    spl = RectBivariateSpline(xs, xs, np.ascontiguousarray(z.T), kx=1, ky=1)
+    return spl(xq, xq).T
+
+
+def crop(field: np.ndarray, X: np.ndarray, npoints_old: int, area_size: float, X_new: np.ndarray) -> np.ndarray:
+    """beam2d.py:419-434 (field on the new grid; the caller rebuilds the grids in between)."""
+    old_X = X[np.abs(X) < area_size / 2]
+    Nc = npoints_old // 2
+    n = len(old_X) // 2
+    old_X = X[Nc - n:Nc + n]
+    win = field[Nc - n:Nc + n, Nc - n:Nc + n]
+    return _interp2d_linear(old_X, np.real(win), X_new) + 1j * _interp2d_linear(old_X, np.imag(win), X_new)
+
+
+def lens_image(field: np.ndarray, X: np.ndarray, Y: np.ndarray, k0: float, f: float, l1: float, l2: float):
+    """beam2d.py:525-535.  ``X`` (and the view ``Y``) is scaled in place, as the reference does."""
+    scale_factor = - l1 / l2
+    xs = X.copy()
+    re, im = np.real(field), np.imag(field)
+    phase = - (X ** 2 + Y ** 2) * k0 * (l1 + l2) / 2 / l2 ** 2
+    X *= scale_factor
+    return scale_factor * (_interp2d_linear(xs, re, X) + 1j * _interp2d_linear(xs, im, X)) * (np.cos(phase) + 1j * np.sin(phase))
+
+
 def modes_synthesize(modes: np.ndarray, coeffs: np.ndarray, npoints: int) -> np.ndarray:
     """beam2d.py:552-562 + :664-666: zero-pad every mode to the grid, sum_i c_i M_i."""
     modes = np.asarray(modes)
@@ -279,6 +324,19 @@ class OracleBeam:
         self.field = coarse(self.field, mean_order)
         self.spectrum = fft2(self.field)
 
+    def crop(self, area_size, npoints=0):
+        X_old, n_old = self.X, self.npoints
+        if npoints:
+            self.npoints = npoints
+        self.area_size = area_size
+        self._grids()
+        self.field = crop(self.field, X_old, n_old, area_size, self.X).astype(self.complex)
+        self.spectrum = fft2(self.field)
+
+    def lens_image(self, f, l1, l2):
+        self.field = lens_image(self.field, self.X, self.Y, self.k0, f, l1, l2).astype(self.complex)
+        self.spectrum = fft2(self.field)
+
     @property
     def iprofile(self):
         return iprofile(self.field)
@@ -299,8 +357,8 @@ class OracleBeam:
     def centroid_intensity(self):
         return centroid_intensity(self.field, self.dL)
 
-    def deconstruct_by_modes(self, modes):
-        return modes_project(self.field, modes)
+    def deconstruct_by_modes(self, modes, mode='scalar'):
+        return modes_lstsq(self.field, modes) if mode == 'lstsq' else modes_project(self.field, modes)
 
     def fast_deconstruct_by_modes(self, modes_matrix_t, modes_matrix_dot_t):
         return modes_fast_lstsq(self.field, modes_matrix_t, modes_matrix_dot_t)
