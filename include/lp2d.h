@@ -88,6 +88,17 @@ LP2D_API int lp2d_fft2(lp2d_plan* plan, const void* in, void* out, long long bat
 LP2D_API int lp2d_propagate(lp2d_plan* plan, void* spectrum, void* field, void* intensity,
                    long long batch, double z, void* stream);
 
+/* A z-sweep in ONE call: nsteps x [propagate(dz)] as lp2d_propagate, and after every step
+ *   probe_out[k][b]  (device, real type, may be NULL) = |field_b[probe_index]|^2, the number the reference's sweep
+ *                    loops read each step (tests/test_analytics.py:43-50, tests/hole_diffraction.py:37-42);
+ *   moments_out[k][b][5] (device, FP64, may be NULL) = [sum I, sum x I, sum y I, sum x^2 I, sum y^2 I] about the
+ *                    grid origin (x = (col - n/2) dL), from which centroid and D4sigma of every step follow
+ *                    (beam2d.py:680-684, 696-702) without a device-to-host round trip per step.
+ * Everything is enqueued on `stream`; the caller synchronises once, after the sweep. */
+LP2D_API int lp2d_propagate_sweep(lp2d_plan* plan, void* spectrum, void* field, long long batch, int nsteps,
+                         double dz, long long probe_index, void* probe_out, double dL, double* moments_out,
+                         void* stream);
+
 /* Fresh chain for ensembles: field_out = ifft2(fft2(field_in) * H(z)) in three
  * passes without materialising the spectrum (unless spectrum_out != NULL, which
  * receives fft2(field_in) * H(z), the spectrum state the reference would hold).

@@ -30,6 +30,7 @@ SIGNATURES = {
     "lp2d_plan_destroy": (_i, [_vp]),
     "lp2d_fft2": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "lp2d_propagate": (_i, [_vp, _vp, _vp, _vp, _ll, _d, _vp]),
+    "lp2d_propagate_sweep": (_i, [_vp, _vp, _vp, _ll, _i, _d, _ll, _vp, _d, _vp, _vp]),
     "lp2d_propagate_field": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _ll, _d, _vp]),
     "lp2d_lens": (_i, [_vp, _vp, _vp, _ll, _d, _d, _vp]),
     "lp2d_mul_fft2": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _vp]),

@@ -303,6 +303,47 @@ class Beam2D:
                        self._batch(), float(z), self._stream())
             self._f = out
 
+    def propagate_sweep(self, dz: float, nsteps: int, probe="centre", moments: bool = False):
+        """``nsteps`` x ``propagate(dz)`` enqueued by ONE library call (extension; the reference's sweeps are Python
+        loops that read ``iprofile[ny, nx]`` or ``centroid`` / ``D4sigma`` every step: tests/test_analytics.py:43-50,
+        tests/gaussbeam_diffraction.py:43-49).  Returns ``(I, M)``: ``I[k]`` = ``iprofile[probe]`` after step k
+        (``probe`` = "centre" -> ``[N/2, N/2]``, an ``(iy, ix)`` pair, or None), and with ``moments=True`` a dict with
+        ``centroid`` (nsteps, 2) and ``D4sigma`` (nsteps, 2) per step, else None.  One synchronisation at the end
+        instead of one per step.  The state after the call is that of the loop (``z`` is advanced ``nsteps`` times)."""
+        torch = _torch()
+        nsteps = int(nsteps)
+        if dz == 0 or nsteps <= 0:
+            return None, None
+        if self._gen is not None or probe is None and not moments:
+            for _ in range(nsteps):
+                self.propagate(dz)
+            return None, None
+        n, B = self.npoints, self._batch()
+        if self._s is None:
+            self._materialise_spectrum()
+        if probe == "centre":
+            probe = (n // 2, n // 2)
+        pidx = -1 if probe is None else int(probe[0]) * n + int(probe[1])
+        pout = None if probe is None else torch.empty(nsteps, B, dtype=self._rdtype, device=self._tdev)
+        mout = torch.empty(nsteps, B, 5, dtype=torch.float64, device=self._tdev) if moments else None
+        out = torch.empty_like(self._s)
+        self._call("lp2d_propagate_sweep", self._plan.handle, self._s.data_ptr(), out.data_ptr(), B, nsteps, float(dz), pidx,
+                   None if pout is None else pout.data_ptr(), float(self.dL), None if mout is None else mout.data_ptr(),
+                   self._stream())
+        self._f = out
+        for _ in range(nsteps):
+            self.z += dz
+        I = None if pout is None else self._output(pout.reshape(nsteps, *self._f.shape[:-2]))
+        M = None
+        if moments:
+            m = mout.cpu().numpy().reshape(nsteps, *self._f.shape[:-2], 5)
+            xc, yc = m[..., 1] / m[..., 0], m[..., 2] / m[..., 0]
+            with np.errstate(invalid="ignore"):
+                sx = np.sqrt(np.maximum(m[..., 3] / m[..., 0] - xc ** 2, 0.0))
+                sy = np.sqrt(np.maximum(m[..., 4] / m[..., 0] - yc ** 2, 0.0))
+            M = {"centroid": np.stack([xc, yc], axis=-1), "D4sigma": 4 * np.stack([sx, sy], axis=-1)}
+        return I, M
+
     def lens(self, f: float):
         """beam2d.py:508-511."""
         torch = _torch()

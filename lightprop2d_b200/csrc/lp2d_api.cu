@@ -58,6 +58,16 @@ static int cuda_fail(cudaError_t e, const char* what) {
     return fail(LP2D_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// probe[b] = |field[b][idx]|^2: what a z-sweep loop reads every step (tests/test_analytics.py:43-50)
+template <typename T>
+__global__ void probe_kernel(const cx<T>* __restrict__ f, T* __restrict__ out, long long plane, long long idx, long long batch) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) {
+        const cx<T> v = f[b * plane + idx];
+        out[b] = v.x * v.x + v.y * v.y;
+    }
+}
+
 // |field|^2, vectorised two samples per thread-iteration
 template <typename T>
 __global__ void intensity_kernel(const cx<T>* __restrict__ f, T* __restrict__ out, long long n) {
@@ -887,6 +897,43 @@ int lp2d_propagate(lp2d_plan* p, void* spectrum, void* field, void* intensity, l
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, intensity, batch, z, s)
                                 : propagate_state<double>(p, spectrum, field, intensity, batch, z, s);
+}
+
+int lp2d_propagate_sweep(lp2d_plan* p, void* spectrum, void* field, long long batch, int nsteps, double dz, long long probe_index,
+                         void* probe_out, double dL, double* moments_out, void* stream) {
+    LP2D_CHECK_2D(p);
+    if (spectrum == nullptr || field == nullptr || batch < 0 || nsteps < 0) return fail(LP2D_EINVAL, "propagate_sweep: NULL pointer or negative count");
+    if (spectrum == field) return fail(LP2D_EINVAL, "propagate_sweep: spectrum and field must be distinct buffers");
+    const long long plane = (long long)p->n * p->n;
+    if (probe_out != nullptr && (probe_index < 0 || probe_index >= plane)) return fail(LP2D_EINVAL, "propagate_sweep: probe_index outside the plane");
+    if (batch == 0 || nsteps == 0 || dz == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t rsz = p->dtype == LP2D_C64 ? sizeof(float) : sizeof(double);
+    for (int k = 0; k < nsteps; ++k) {
+        const int rc = p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, nullptr, batch, dz, s)
+                                            : propagate_state<double>(p, spectrum, field, nullptr, batch, dz, s);
+        if (rc) return rc;
+        if (probe_out != nullptr) {
+            char* dst = static_cast<char*>(probe_out) + (size_t)k * batch * rsz;
+            const unsigned blocks = (unsigned)((batch + 127) / 128);
+            if (p->dtype == LP2D_C64)
+                probe_kernel<float><<<blocks, 128, 0, s>>>(static_cast<const float2*>(field), reinterpret_cast<float*>(dst), plane, probe_index, batch);
+            else
+                probe_kernel<double><<<blocks, 128, 0, s>>>(static_cast<const double2*>(field), reinterpret_cast<double*>(dst), plane, probe_index, batch);
+            ++g_launches;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "probe launch");
+        }
+        if (moments_out != nullptr) {
+            const size_t csz = p->dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2);
+            for (long long b = 0; b < batch; ++b) {
+                const int rc2 = lp2d_moments(p->dtype, static_cast<const char*>(field) + (size_t)b * plane * csz, p->n, dL, 0.0, 0.0,
+                                             moments_out + ((size_t)k * batch + b) * 5, stream);
+                if (rc2) return rc2;
+            }
+        }
+    }
+    return LP2D_OK;
 }
 
 int lp2d_propagate_field(lp2d_plan* p, const void* field_in, void* field_out, void* spectrum_out, void* intensity,

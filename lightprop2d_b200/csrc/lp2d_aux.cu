@@ -11,6 +11,8 @@ namespace lp2d {
 int set_error(int code, const std::string& msg);   // lp2d_api.cu
 int modes_project_tc(const void* field, const void* modes, void* coeffs, int n, int nb, int nmodes, long long batch,
                      cudaStream_t s);              // lp2d_modes_tc.cu
+int modes_synthesize_tc(const void* coeffs, const void* modes, void* field, int n, int nb, int nmodes, long long batch,
+                        cudaStream_t s);           // lp2d_modes_tc.cu
 
 // out[b][r][c] = in[b][clamp(r-pad)][clamp(c-pad)]      (beam2d.py:392-401)
 template <typename T>
@@ -451,6 +453,14 @@ int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void
         return set_error(LP2D_EINVAL, "modes_synthesize: bad arguments");
     if (batch == 0) return LP2D_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == LP2D_C64) {
+        // tensor-core form (tcgen05, 3xTF32) when the crop is made of whole 32-point runs
+        const char* env = getenv("LP2D_MODES_TC");
+        if (env == nullptr || atoi(env) != 0) {
+            const int rc = modes_synthesize_tc(coeffs, modes, field, n, nb, nmodes, batch, s);
+            if (rc != LP2D_EUNSUPPORTED) return rc;
+        }
+    }
     const unsigned gx = (unsigned)(((long long)n * n + 255) / 256);
     if (dtype == LP2D_C64) {
         constexpr int BT = 8;

@@ -317,6 +317,192 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) modes_project_tc_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Mode synthesis on the tensor cores:  field_b[crop(p)] = sum_m coeffs[b][m] * modes[m][p]   (beam2d.py:552-562, 664-666)
+//
+// The same real TF32 GEMM with the roles changed: UMMA M = 128 grid points p (the big dimension, nb^2 of them), N = 2 * 64
+// (beam, re / im), K = 2 * nmodes (the reduction runs over the modes).  Per K block of 16 modes the producers read
+// 128 points x 16 modes of the mode matrix (every warp load = 32 consecutive points of one mode: 256 contiguous bytes)
+// and 64 beams x 16 coefficients, split them hi / lo and stage them in the SAME canonical K-major tiles as the projection
+// kernel: A row p = (Mr, Mi) of the block's modes, B rows (2b, 2b+1) = (Cr, -Ci), (Ci, Cr).  The MMA warp, the
+// descriptors, the 3xTF32 products and the chain flush are shared with the projection.  No split-K: a CTA owns a tile of
+// 128 points x 64 beams for all modes and stores its result straight from the TMEM read-back (consecutive lanes =
+// consecutive points of one beam: coalesced 8-byte stores).  SIMT needs 8 * batch * nmodes * nb^2 real FMAs on the FP32
+// pipes (34 GFLOP at config 5: 1.49 ms measured); here the mode matrix streams once at tensor-core speed.
+struct SynthArgs {
+    const float2* coeffs;   // batch x nmodes
+    const float2* modes;    // nmodes x nb*nb
+    float2* field;          // batch x n x n (zero-filled by the caller outside the crop)
+    int n, nb, nmodes, batch;
+    int kblocks;            // ceil(nmodes / KB)
+    int ptiles, btiles;
+};
+
+__global__ void __launch_bounds__(CTA_THREADS, 1) modes_synth_tc_kernel(const SynthArgs p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t s_full[STAGES];
+    __shared__ uint64_t s_empty[STAGES];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    const int pt_tile = blockIdx.x % p.ptiles, bt = blockIdx.x / p.ptiles;
+    const long long p0 = (long long)pt_tile * UM;
+    const int b0 = bt * BT;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    const long long kk = (long long)p.nb * p.nb;
+    // A: thread = (point pt, mode quad g): modes kb*KB + 4g .. 4g+3 of point p0 + pt -> chunks 2g, 2g+1 of row pt
+    const int a_pt = tid & (UM - 1), a_g = tid >> 7;
+    const float2* a_src = p.modes + p0 + a_pt;
+    const uint32_t a_off = (uint32_t)((2 * a_g) * CH_A + a_pt * 16);
+    // B: thread = (beam row, chunk c): coefficients kb*KB + 2c, 2c+1 of beam b0 + row
+    const int b_row = tid / CHUNKS, b_c = tid % CHUNKS;
+    const bool b_ok = (b0 + b_row < p.batch);
+    const float2* b_src = p.coeffs + (long long)(b_ok ? b0 + b_row : 0) * p.nmodes + 2 * b_c;
+    const uint32_t b_off = (uint32_t)(b_c * CH_B + (2 * b_row) * 16);
+
+    float2 ra[PF][4], rb[PF][2];
+    int ld_kb = 0;
+    auto load_block = [&](auto set_c) {
+        constexpr int SET = decltype(set_c)::value;
+        const int m0 = ld_kb * KB;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + 4 * a_g + j;
+            ra[SET][j] = (m < p.nmodes) ? __ldcs(a_src + (long long)m * kk) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m = m0 + 2 * b_c + j;
+            rb[SET][j] = (b_ok && m < p.nmodes) ? __ldg(b_src + m0 + j) : make_float2(0.f, 0.f);
+        }
+        ++ld_kb;
+    };
+    auto store_block = [&](int stage, auto set_c) {
+        constexpr int SET = decltype(set_c)::value;
+        unsigned char* a_hi = smem + stage * STAGE_BYTES;
+        unsigned char* a_lo = a_hi + TILE_A;
+        unsigned char* b_hi = a_lo + TILE_A;
+        unsigned char* b_lo = b_hi + TILE_B;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float4 h, l;
+            split_tf32(ra[SET][2 * c].x, h.x, l.x); split_tf32(ra[SET][2 * c].y, h.y, l.y);
+            split_tf32(ra[SET][2 * c + 1].x, h.z, l.z); split_tf32(ra[SET][2 * c + 1].y, h.w, l.w);
+            *reinterpret_cast<float4*>(a_hi + a_off + c * CH_A) = h;
+            *reinterpret_cast<float4*>(a_lo + a_off + c * CH_A) = l;
+        }
+        {
+            float4 h, l;
+            split_tf32(rb[SET][0].x, h.x, l.x); split_tf32(rb[SET][0].y, h.y, l.y);
+            split_tf32(rb[SET][1].x, h.z, l.z); split_tf32(rb[SET][1].y, h.w, l.w);
+            *reinterpret_cast<float4*>(b_hi + b_off) = make_float4(h.x, -h.y, h.z, -h.w);
+            *reinterpret_cast<float4*>(b_lo + b_off) = make_float4(l.x, -l.y, l.z, -l.w);
+            *reinterpret_cast<float4*>(b_hi + b_off + 16) = make_float4(h.y, h.x, h.w, h.z);
+            *reinterpret_cast<float4*>(b_lo + b_off + 16) = make_float4(l.y, l.x, l.w, l.z);
+        }
+    };
+
+    float acc[ACC];
+#pragma unroll
+    for (int j = 0; j < ACC; ++j) acc[j] = 0.f;
+    const int col0 = (warp >> 2) * ACC;
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+    auto flush = [&]() {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int c0 = 0; c0 < ACC; c0 += 16) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(tlane + (uint32_t)c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    const int nblocks = p.kblocks;
+    if (warp == THREADS / 32) {
+        if ((tid & 31) == 0) {
+            for (int i = 0; i < nblocks; ++i) {
+                const int stage = i % STAGES;
+                const bool fresh = (i % FLUSH) == 0;
+                mbar_wait(&s_full[stage], (uint32_t)((i / STAGES) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES), sa_lo = sa_hi + TILE_A, sb_hi = sa_lo + TILE_A, sb_lo = sb_hi + TILE_B;
+#pragma unroll
+                for (int s = 0; s < CHUNKS / 2; ++s) {
+                    const uint64_t dah = umma_desc(sa_hi + 2 * s * CH_A, CH_A, 128), dal = umma_desc(sa_lo + 2 * s * CH_A, CH_A, 128);
+                    const uint64_t dbh = umma_desc(sb_hi + 2 * s * CH_B, CH_B, 128), dbl = umma_desc(sb_lo + 2 * s * CH_B, CH_B, 128);
+                    mma_tf32(tmem, dah, dbh, (!fresh || s > 0) ? 1u : 0u);
+                    mma_tf32(tmem, dah, dbl, 1u);
+                    mma_tf32(tmem, dal, dbh, 1u);
+                }
+                umma_commit(&s_empty[stage]);
+            }
+        }
+    } else {
+        auto step = [&](int i, auto set_c) {
+            const int stage = i % STAGES;
+            if ((i % FLUSH) == 0 && i > 0) {
+                mbar_wait(&s_empty[(i - 1) % STAGES], (uint32_t)(((i - 1) / STAGES) & 1));
+                flush();
+            }
+            if (i >= STAGES) mbar_wait(&s_empty[stage], (uint32_t)((i / STAGES - 1) & 1));
+            store_block(stage, set_c);
+            if (i + PF < nblocks) load_block(set_c);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+            if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[stage])) : "memory");
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        if (0 < nblocks) load_block(I0{});
+        if (1 < nblocks) load_block(I1{});
+        for (int i = 0; i < nblocks; i += 2) {
+            step(i, I0{});
+            if (i + 1 < nblocks) step(i + 1, I1{});
+        }
+    }
+    if (nblocks > 0 && warp < THREADS / 32) {
+        mbar_wait(&s_empty[(nblocks - 1) % STAGES], (uint32_t)(((nblocks - 1) / STAGES) & 1));
+        flush();
+        // epilogue: TMEM lane = point p0 + 32*(warp%4) + lane-in-warp, columns = (beam, re / im)
+        const long long pp = p0 + (warp & 3) * 32 + (tid & 31);
+        const int cy = (int)(pp / p.nb), cx = (int)(pp % p.nb);
+        const int dn = (p.n - p.nb) / 2;
+        float2* dst = p.field + (long long)(cy + dn) * p.n + (cx + dn);
+        const long long plane = (long long)p.n * p.n;
+#pragma unroll
+        for (int j = 0; j < ACC; j += 2) {
+            const int b = b0 + ((col0 + j) >> 1);
+            if (b < p.batch) __stcs(dst + (long long)b * plane, make_float2(acc[j], acc[j + 1]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace tc
 
 // complex64 only; nb must be a multiple of the K block.  Returns LP2D_EUNSUPPORTED when the shape
@@ -354,6 +540,35 @@ int modes_project_tc(const void* field, const void* modes, void* coeffs, int n, 
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project_tc launch: ") + cudaGetErrorString(e));
+    return LP2D_OK;
+}
+
+// complex64 only; the crop must be made of whole 32-point runs (nb % 32 == 0, nb^2 % 128 == 0).  Returns
+// LP2D_EUNSUPPORTED when the shape is not covered (the caller then uses the SIMT kernel).
+int modes_synthesize_tc(const void* coeffs, const void* modes, void* field, int n, int nb, int nmodes, long long batch, cudaStream_t s) {
+    using namespace tc;
+    if (nb % 32 != 0 || ((long long)nb * nb) % UM != 0 || nmodes < 1) return LP2D_EUNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(modes_synth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_synthesize_tc setup: ") + cudaGetErrorString(e));
+        configured = true;
+    }
+    SynthArgs a;
+    a.coeffs = static_cast<const float2*>(coeffs);
+    a.modes = static_cast<const float2*>(modes);
+    a.field = static_cast<float2*>(field);
+    a.n = n; a.nb = nb; a.nmodes = nmodes; a.batch = (int)batch;
+    a.kblocks = (nmodes + KB - 1) / KB;
+    a.ptiles = (int)(((long long)nb * nb) / UM);
+    a.btiles = (int)((batch + BT - 1) / BT);
+    cudaError_t e = cudaSuccess;
+    if (nb != n) e = cudaMemsetAsync(field, 0, sizeof(float2) * (size_t)batch * n * n, s);     // zero padding around the crop
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_synthesize_tc memset: ") + cudaGetErrorString(e));
+    modes_synth_tc_kernel<<<(unsigned)((long long)a.ptiles * a.btiles), CTA_THREADS, SMEM_BYTES, s>>>(a);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_synthesize_tc launch: ") + cudaGetErrorString(e));
     return LP2D_OK;
 }
 

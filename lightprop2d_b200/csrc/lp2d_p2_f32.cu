@@ -16,9 +16,6 @@ static const P2Ops<float> kP2F32[] = {
     T3Inst<float, 1024, 32, 8, 2, 3>::entry(),
     T3Inst<float, 1024, 32, 8, 2, 0>::entry(),
     T3Inst<float, 1024, 32, 4, 3>::entry(),
-    T3Inst<float, 1024, 32, 8, 2, 1>::entry(),
-    T3Inst<float, 1024, 32, 8, 2, 2>::entry(),
-    T3Inst<float, 1024, 32, 4, 3, 3>::entry(),
     T3Inst<float, 512, 32, 8, 3>::entry(),
     T3Inst<float, 512, 32, 16, 2>::entry(),
     T3Inst<float, 256, 16, 16, 4>::entry(),

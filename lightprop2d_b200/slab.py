@@ -179,6 +179,35 @@ def exchange_transpose(x, backend, group=None, tiles=False):
     return recv.permute(1, 0, 2).reshape(nb, n).contiguous()
 
 
+def exchange_transpose_chunked(first_pass, rows, n, backend, group=None, chunks=4):
+    """The first line pass and the all-to-all transpose, OVERLAPPED: the slab's ``rows`` lines are transformed in
+    ``chunks`` groups; as soon as a group is transformed and packed its tiles go out (``dist.all_to_all`` of G
+    tiles, asynchronous on the communication stream) while the next group is being transformed.  The receive buffer
+    is laid out so that the second pass reads it in place (``lp2d_pass_lines_tiles`` with tile = rows / chunks):
+    tile index ``q * chunks + c`` = lines ``c * L .. (c+1) * L`` of sender ``q``.  ``first_pass(lo, hi)`` returns
+    the transformed lines ``lo .. hi`` of this rank's slab, shape ``(hi - lo, n)``."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rows * world != n or rows % chunks:
+        raise ValueError(f"slab of {rows} lines: not {n} / {world}, or not divisible into {chunks} chunks")
+    L = rows // chunks
+    recv = backend.empty(world, chunks, rows, L)
+    works = []
+    for c in range(chunks):
+        part = first_pass(c * L, (c + 1) * L)                       # (L, n)
+        send = backend.pack_transpose(part, rows)                   # (world, rows, L): [q][i][r'] = part[r'][q*rows + i]
+        if world == 1:
+            recv[0, c].copy_(send[0])
+        else:
+            works.append(dist.all_to_all([recv[q, c] for q in range(world)], [send[q] for q in range(world)],
+                                         group=group, async_op=True))
+            works.append(send)                                      # keep the send buffer alive until the wait
+    for w in works:
+        if hasattr(w, "wait"):
+            w.wait()
+    return recv.reshape(world * chunks, rows, L)
+
+
 class SlabBeam2D:
     """``Beam2D`` semantics (field, spectrum, ``propagate``, ``iprofile``) for ONE grid spread over the
     ranks of a process group.  ``init_field_gen(X, Y_slab, *args)`` is called with the full 1-D ``X`` and
@@ -186,7 +215,7 @@ class SlabBeam2D:
     beam2d.py:119-120), or ``init_field`` gives this rank's ``(N/G, N)`` rows."""
 
     def __init__(self, area_size, npoints, wl, init_field=None, init_field_gen=None, init_gen_args=(),
-                 complex_bits=64, group=None, backend=None, device=None):
+                 complex_bits=64, group=None, backend=None, device=None, chunks=None):
         import torch
         import torch.distributed as dist
         self.group = group
@@ -196,6 +225,16 @@ class SlabBeam2D:
         self.z = 0.
         self.r0, self.r1 = slab_rows(self.npoints, self.rank, self.world)
         self.backend = backend if backend is not None else CudaLineBackend(area_size, npoints, wl, complex_bits, device)
+        # overlap of the first pass with the exchange: groups of lines per all-to-all (1 = one exchange after the
+        # whole pass).  Default: 4 on several GPUs with the CUDA backend (measured: profiles/r2c_slab_*.json)
+        if chunks is None:
+            import os
+            env = os.environ.get("LP2D_SLAB_CHUNKS")
+            chunks = int(env) if env else (4 if (self.world > 1 and backend is None) else 1)
+        nb_ = self.npoints // self.world
+        while chunks > 1 and (nb_ % chunks or (nb_ // chunks) & (nb_ // chunks - 1)):
+            chunks //= 2
+        self.chunks = max(1, int(chunks))
         self.dL = area_size / npoints                                       # beam2d.py:299
         self.X = np.arange(-npoints // 2, npoints // 2, 1) * self.dL        # :300-301
         self.Y = self.X.reshape((-1, 1))[self.r0:self.r1]                   # this rank's rows of :302
@@ -217,6 +256,10 @@ class SlabBeam2D:
 
     # forward 2-D transform: field rows -> transposed spectrum columns
     def _fft2(self, field):
+        if self.chunks > 1:
+            cols = exchange_transpose_chunked(lambda lo, hi: self.backend.lines(field[lo:hi], self.r0 + lo),
+                                              int(field.shape[0]), self.npoints, self.backend, self.group, self.chunks)
+            return self.backend.lines(cols, self.r0, transposed=True)
         rows = self.backend.lines(field, self.r0)                            # FFT along x
         cols = exchange_transpose(rows, self.backend, self.group, tiles=True)  # this rank's grid columns, as lines
         return self.backend.lines(cols, self.r0, transposed=True)            # FFT along y
@@ -227,16 +270,27 @@ class SlabBeam2D:
             return None
         self.z += z
         # spectrum *= H (state kept, transposed layout) and inverse transform along y, one local pass
-        cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True, z=z, state_out=self.spectrum_t)
-        rows = exchange_transpose(cols, self.backend, self.group, tiles=True)
+        if self.chunks > 1:
+            st = self.spectrum_t
+            rows = exchange_transpose_chunked(
+                lambda lo, hi: self.backend.lines(st[lo:hi], self.r0 + lo, inverse=True, transposed=True, z=z, state_out=st[lo:hi]),
+                int(st.shape[0]), self.npoints, self.backend, self.group, self.chunks)
+        else:
+            cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True, z=z, state_out=self.spectrum_t)
+            rows = exchange_transpose(cols, self.backend, self.group, tiles=True)
         inten = self.backend.empty(*self.field.shape, real=True) if intensity else None
         self.field = self.backend.lines(rows, self.r0, inverse=True, intensity=inten, out=self.field)
         return inten
 
     def _ifft2(self):
         """field = ifft2(spectrum) from the transposed spectrum slab (no H): the second half of ``propagate``."""
-        cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True)
-        rows = exchange_transpose(cols, self.backend, self.group, tiles=True)
+        if self.chunks > 1:
+            st = self.spectrum_t
+            rows = exchange_transpose_chunked(lambda lo, hi: self.backend.lines(st[lo:hi], self.r0 + lo, inverse=True, transposed=True),
+                                              int(st.shape[0]), self.npoints, self.backend, self.group, self.chunks)
+        else:
+            cols = self.backend.lines(self.spectrum_t, self.r0, inverse=True, transposed=True)
+            rows = exchange_transpose(cols, self.backend, self.group, tiles=True)
         self.field = self.backend.lines(rows, self.r0, inverse=True, out=self.field)
 
     def lens(self, f: float):

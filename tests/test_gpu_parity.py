@@ -177,6 +177,31 @@ def test_golden_gauss_axis(bits):
     assert np.max(np.abs(i0 * (1 + zn ** 2) - 1)) < (1e-5 if bits == 64 else 1e-8)
 
 
+@pytest.mark.parametrize("bits", BITS)
+def test_sweep_in_one_call_equals_the_loop(bits):
+    """propagate_sweep (one library call, one synchronisation) against the reference-generated on-axis series and
+    against the step-by-step loop: field, z, probe, centroid and D4sigma of every step."""
+    g = golden(f"gauss_axis_c{bits}")
+    area, n, wl, R, dz = g["params"]
+    n = int(n)
+    b = Beam2D(area, n, wl, init_field_gen=lp.gaussian_beam, init_gen_args=(1., R, 0.004, -0.002), complex_bits=bits)
+    c = Beam2D(area, n, wl, init_field_gen=lp.gaussian_beam, init_gen_args=(1., R, 0.004, -0.002), complex_bits=bits)
+    I, M = b.propagate_sweep(dz, 12, probe=(n // 2 + 3, n // 2 - 5), moments=True)
+    for k in range(12):
+        c.propagate(dz)
+        assert np.allclose(I[k], c.iprofile[n // 2 + 3, n // 2 - 5], rtol=1e-6 if bits == 64 else 1e-13)
+        assert np.allclose(M["centroid"][k], c.centroid[:2], rtol=1e-5 if bits == 64 else 1e-9, atol=1e-9)
+        assert np.allclose(M["D4sigma"][k], c.D4sigma, rtol=1e-5 if bits == 64 else 1e-9)
+    # (the loop's first step runs the fused fft2 -> H -> ifft2 chain, the sweep fft2 then the stateful step: same
+    # values up to rounding, not bit for bit)
+    assert b.z == c.z
+    assert rel_l2(b.field, c.field) <= (2e-6 if bits == 64 else 1e-14)
+    assert rel_l2(b.spectrum, c.spectrum) <= (2e-6 if bits == 64 else 1e-14)
+    a = Beam2D(area, n, wl, init_field_gen=lp.gaussian_beam, init_gen_args=(1., R), complex_bits=bits)
+    i0, _ = a.propagate_sweep(dz, 40)
+    assert np.allclose(np.ravel(i0), g["i0"], rtol=2e-5 if bits == 64 else 1e-11)
+
+
 def test_golden_update_obj():
     g = golden("update_obj")
     np.random.seed(7)
@@ -544,8 +569,9 @@ def test_cabi_passes_compose_to_fft2(bits):
 
 # ----------------------------------------------------------------------------- slab passes (one GPU)
 @pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [1, 4])
 @pytest.mark.parametrize("bits,n", [(64, 256), (64, 1024), (128, 512)])
-def test_slab_single_rank_matches_oracle(bits, n, tol):
+def test_slab_single_rank_matches_oracle(bits, n, chunks, tol):
     """SlabBeam2D with one slab = the whole grid: lp2d_pass_lines, the transposed-orientation plan and
     lp2d_pack_transpose against the oracle (the exchange itself is covered by tests/test_dist_gloo.py
     and tools/slab_multi_gpu.py)."""
@@ -555,7 +581,10 @@ def test_slab_single_rank_matches_oracle(bits, n, tol):
     ct = np.complex64 if bits == 64 else np.complex128
     f0 = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(ct)
     area, wl = 200 * lp.um * n / 256, 632 * lp.nm
-    b = SlabBeam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+    # chunks > 1: the first pass in groups of lines, each group packed and "exchanged" (a local copy on one rank) into
+    # the tile layout the second pass reads in place -- the overlap form used on several GPUs
+    b = SlabBeam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits, chunks=chunks)
+    assert b.chunks == chunks
     o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
     assert rel_l2(b.gather_spectrum().cpu().numpy(), o.spectrum) <= tol[bits]
     inten = b.propagate(100 * lp.um, intensity=True)

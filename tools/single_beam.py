@@ -40,6 +40,12 @@ for bits in (64, 128):
             b.propagate(0.02)
         host = (time.perf_counter() - t0) / 200 * 1e6
         torch.cuda.synchronize()
+        b.propagate_sweep(0.02, 20)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b.propagate_sweep(0.02, 500, probe="centre")
+        torch.cuda.synchronize()
+        sweep = (time.perf_counter() - t0) / 500 * 1e6
         P = n * n * (8 if bits == 64 else 16)
-        print(f"c{bits} n={n:5d}: Beam2D.propagate {t_py:8.1f} us  C ABI {t_c:8.1f} us  host-side {host:6.1f} us/call  roofline(3PB) {3*P/6535e9*1e6:7.1f} us", flush=True)
+        print(f"c{bits} n={n:5d}: Beam2D.propagate {t_py:8.1f} us  C ABI {t_c:8.1f} us  host-side {host:6.1f} us/call  sweep(one call, incl. probe) {sweep:6.1f} us/step  roofline(3PB) {3*P/6535e9*1e6:7.1f} us", flush=True)
         del b
