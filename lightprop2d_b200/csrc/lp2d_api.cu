@@ -337,6 +337,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     // and, for the small planes, on more of them (profiles/r1c_size_sweep.log, r1c_group_sweep.log):
     //   complex64 256: + plain fft2; complex64 512 and complex128 256: every step
     int ops_default = 2;                            // (also complex64 2048: the steps with a state store only)
+    // round 2 (profiles/r2c_sweep_final.log): at 1024 complex64 every step -- plain fft2 on the persistent form
+    // (4.83 vs 7.0 us per beam per-pass), the fresh chain on the ticket form (10.8 vs 13.7)
+    if (dtype == LP2D_C64 && n == 1024) ops_default = 7;
     if (dtype == LP2D_C64 && n == 256) ops_default = 3;
     if ((dtype == LP2D_C64 && n == 512) || (dtype == LP2D_C128 && n == 256)) ops_default = 7;
     env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : ops_default;

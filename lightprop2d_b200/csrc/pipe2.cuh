@@ -98,7 +98,8 @@ __device__ __forceinline__ void p2_signal_consumed(unsigned int* ctr) {
 // L2 eviction priorities: user planes are streamed (evict first), the ring is kept (evict last)
 enum { P2_HINT_KEEP_RING = 2,        // bit 0 was the (dropped) hint on the cp.async path
        P2_HINT_PREFETCH = 4,         // speculative L2 prefetch of the user rows of item blockIdx.x while the ticket is drawn
-       P2_HINT_LATE_DRAW = 8 };      // persistent form: draw the next ticket when an item is finished, not when its tile is read
+       P2_HINT_LATE_DRAW = 8,
+       P2_HINT_RELAXED_POLL = 16 };  // experiment: relaxed instead of acquire loads on the dependency counters (no L1 invalidation)      // persistent form: draw the next ticket when an item is finished, not when its tile is read
 // KIND is a compile-time value: a policy selected at run time ends up in a misaligned uniform
 // register pair (ptxas 12.9) and the copy traps as an illegal instruction.
 template <int KIND>     // 0 no hint, 1 evict first, 2 evict last
@@ -149,9 +150,17 @@ __device__ __forceinline__ void p2_poll(const P2Args<T>& p, int item, unsigned i
     // acquire reads: everything that is read once the counters are complete (the ring) is requested only
     // after a CTA barrier that follows the test of these values, and was made visible before the counter
     // was incremented (red.release)
-    if (it.s > 0) pa = p2_ld_relaxed(&done[(it.s - 1) * p.ngroups + it.g]);
-    if (st.out_ring && !st.in_ring && it.g >= p.ring_slots)
-        pb = p2_ld_relaxed(&done[(p.nstages - 1) * p.ngroups + (it.g - p.ring_slots)]);
+    const bool rlx = (p.hints & P2_HINT_RELAXED_POLL) != 0;
+    if (it.s > 0) {
+        const unsigned int* c = &done[(it.s - 1) * p.ngroups + it.g];
+        if (rlx) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pa) : "l"(c) : "memory");
+        else pa = p2_ld_relaxed(c);
+    }
+    if (st.out_ring && !st.in_ring && it.g >= p.ring_slots) {
+        const unsigned int* c = &done[(p.nstages - 1) * p.ngroups + (it.g - p.ring_slots)];
+        if (rlx) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pb) : "l"(c) : "memory");
+        else pb = p2_ld_relaxed(c);
+    }
 }
 template <typename T, int TILES>
 __device__ __forceinline__ bool p2_ready(const P2Args<T>& p, int item, unsigned int full) {
@@ -179,6 +188,61 @@ __device__ __forceinline__ int p2_fac_index(int map, int pos, int m) {
     if (map == P2_MAP_FREQ) return (m < E / 2) ? pos : N - pos;
     if (map == P2_MAP_FULL) return pos;
     return (m < E / 2) ? N / 2 - pos : pos - N / 2;
+}
+
+__device__ __forceinline__ float2 p2_shfl(float2 v, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ double2 p2_shfl(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+// v[m] *= factor(line position t + TPL*m) from the folded factor row of the line, for a ROW item.
+// One warp per line (TPL = 32): the fold makes the factor of position pos equal to the one of N - pos (resp. of the
+// mirror image about N/2), so a lane needs E/2 values of its own (index t + 32 j) and E/2 values that lane 32 - t holds
+// (index 32 (j+1) - t): E/2 loads in ONE batch and E/2 shuffles instead of E loads in four dependent batches (the four
+// L2 round trips were a sixth of a CTA's life in the ticket form).  Lane 0 is its own mirror, shifted by one (and needs
+// the single unpaired entry N/2).  Unfolded plane / other thread shapes: plain loads, eight at a time.
+template <typename T, int N, int E, int GB>
+__device__ __forceinline__ void p2_apply_factor_row(cx<T> (&v)[E], const cx<T>* __restrict__ fline, int map, int t) {
+    constexpr int TPL = N / E, H = E / 2;
+    if (TPL != 32 || sizeof(T) != 4 || map == P2_MAP_FULL) {      // (complex128: four shuffles per value, measured slower)
+#pragma unroll
+        for (int m0 = 0; m0 < E; m0 += 8) {
+            cx<T> h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (m0 + i < E) h[i] = __ldcg(&fline[p2_fac_index<N, E>(map, t + TPL * (m0 + i), m0 + i)]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (m0 + i < E) v[m0 + i] = cmul(v[m0 + i], h[i]);
+            if (E > 16) asm volatile("" ::: "memory");
+        }
+        return;
+    }
+    cx<T> gx = mk<T>((T)0, (T)0);
+    if (t == 0) gx = __ldcg(fline + N / 2);
+    const int src = (TPL - t) & (TPL - 1);
+    // GB values per batch: all E/2 at once where the registers allow it (persistent form), two batches otherwise
+#pragma unroll
+    for (int j0 = 0; j0 < H; j0 += GB) {
+        cx<T> g[GB + 1];
+#pragma unroll
+        for (int i = 0; i <= GB; ++i)                                   // (lane 0 needs g[j + 1]: one value of overlap)
+            if (i < GB || j0 + GB < H) g[i] = (i < GB || t == 0) ? __ldcg(fline + t + TPL * (j0 + i)) : mk<T>((T)0, (T)0);
+#pragma unroll
+        for (int i = 0; i < GB; ++i) {
+            const int j = j0 + i;
+            cx<T> mv = p2_shfl(g[i], src);
+            if (t == 0) mv = (j + 1 < H) ? g[i + 1] : gx;
+            if (map == P2_MAP_FREQ) {
+                v[j] = cmul(v[j], g[i]);                                // position t + 32 j
+                v[E - 1 - j] = cmul(v[E - 1 - j], mv);                  // position t + 32 (E-1-j): index N - pos = 32 (j+1) - t
+            } else {
+                v[H + j] = cmul(v[H + j], g[i]);                        // position N/2 + t + 32 j: index pos - N/2
+                v[H - 1 - j] = cmul(v[H - 1 - j], mv);                  // position t + 32 (H-1-j): index N/2 - pos = 32 (j+1) - t
+            }
+        }
+        if (GB < H) asm volatile("" ::: "memory");
+    }
 }
 
 template <typename T>
@@ -231,12 +295,12 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
     const int nb = left < p.G ? (int)left : p.G;
     const int fixed = it.tile * W + l;
     const long long off0 = (AXIS == AX_ROW) ? (long long)fixed * N : fixed;
-    const long long o_first = (REV ? (long long)((N - t) & (N - 1)) : (long long)t) * PSTRIDE;
-    const long long o_base = (REV ? (long long)(N - t) : (long long)t) * PSTRIDE;
-    constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * PSTRIDE;
+    // (offsets inside a plane fit 32 bits: fewer live registers across the transform than 64-bit ones)
+    const int o_first = (REV ? ((N - t) & (N - 1)) : t) * (int)PSTRIDE;
+    const int o_base = (REV ? (N - t) : t) * (int)PSTRIDE;
+    constexpr int o_step = (REV ? -TPL : TPL) * (int)PSTRIDE;
     const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
     const cx<T>* fline = p.fac + (long long)fixed * p.fac_stride;   // L2-resident factor row of this line
-    const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
 
     for (int bi = 0; bi < nb; ++bi) {
         const long long b = b0 + bi;
@@ -251,15 +315,18 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
                 for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
             }
             if (use_pre) {
-                // eight factors at a time (32 loads in flight would double the register footprint)
+                if constexpr (AXIS == AX_ROW) {
+                    p2_apply_factor_row<T, N, E, (E / 2 < 8 ? E / 2 : 8)>(v, fline, p.fac_map, t);
+                } else {
 #pragma unroll
-                for (int m0 = 0; m0 < E; m0 += 8) {
-                    cx<T> h[8];
+                    for (int m0 = 0; m0 < E; m0 += 8) {
+                        cx<T> h[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) if (m0 + i < E) h[i] = __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * (m0 + i), m0 + i)]);
+                        for (int i = 0; i < 8; ++i) if (m0 + i < E) h[i] = __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * (m0 + i), m0 + i)]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) if (m0 + i < E) v[m0 + i] = cmul(v[m0 + i], h[i]);
-                    if (E > 16) asm volatile("" ::: "memory");
+                        for (int i = 0; i < 8; ++i) if (m0 + i < E) v[m0 + i] = cmul(v[m0 + i], h[i]);
+                        if (E > 16) asm volatile("" ::: "memory");
+                    }
                 }
             }
         }
@@ -270,19 +337,16 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
         auto pre_hook = [&](int m, const cx<T>& val) {
             if (pre_dst != nullptr) __stcs(pre_dst + (TPL * m) * PSTRIDE, val);
         };
-        cx<T>* const ring_dst = OUT_RING ? p.ring + (slot0 + bi) * PLANE + off0 : nullptr;
-        cx<T>* const out_dst = (!OUT_RING && st.out != nullptr) ? st.out + b * PLANE + off0 : nullptr;
-        T* const inten_dst = (!OUT_RING && st.inten != nullptr) ? st.inten + b * PLANE + off0 : nullptr;
-        const T scale = st.scale;
+        // (destinations are formed where they are used: with the bursts that is after the transform, and nothing but
+        // the plane offset has to stay in registers across it)
         auto post_hook = [&](int m, const cx<T>& val0) {
-            const cx<T> val = cscale(val0, scale);          // (a scale of 1 is exact)
-            const long long o = (m == 0) ? o_first : o_base + m * o_step;
+            const cx<T> val = cscale(val0, st.scale);       // (a scale of 1 is exact)
+            const int o = (m == 0) ? o_first : o_base + m * o_step;
             if constexpr (OUT_RING) {
-                if (keep_ring) p2_st_ring<2>(ring_dst + o, val);
-                else p2_st_ring<0>(ring_dst + o, val);
+                p2_st_ring<2>(p.ring + (slot0 + bi) * PLANE + off0 + o, val);     // L2 evict-last: re-read by the next stage
             } else {
-                if (out_dst != nullptr) __stcs(out_dst + o, val);
-                if (inten_dst != nullptr) __stcs(inten_dst + o, val.x * val.x + val.y * val.y);
+                if (st.out != nullptr) __stcs(st.out + b * PLANE + off0 + o, val);
+                if (st.inten != nullptr) __stcs(st.inten + b * PLANE + off0 + o, val.x * val.x + val.y * val.y);
             }
         };
         // HOOKS bit 0: state stores inside the first radix pass, bit 1: result stores inside the last one; otherwise

@@ -151,30 +151,21 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
     const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
 
     cx<T> v[E];
-    if (use_pre) {
-        // the factors come from L2 (a few hundred cycles): ask for all of them before the tile is touched
-        cx<T> h[E];
 #pragma unroll
-        for (int m = 0; m < E; ++m) h[m] = __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]);
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
-        if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
+    for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
+    if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
+    if constexpr (!IN_RING) {
         if (st.mask_kind != MASK_NONE) {
             const long long mb = b * st.mask_beam_stride + off0;
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
         }
+        if (use_pre) {
+            if constexpr (AXIS == AX_ROW) {
+                p2_apply_factor_row<T, N, E, E / 2>(v, fline, p.fac_map, t);
+            } else {
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], h[m]);
-    } else {
-#pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
-        if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
-        if constexpr (!IN_RING) {
-            if (st.mask_kind != MASK_NONE) {
-                const long long mb = b * st.mask_beam_stride + off0;
-#pragma unroll
-                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], __ldcg(&fline[p2_fac_index<N, E>(p.fac_map, t + TPL * m, m)]));
             }
         }
     }
