@@ -36,7 +36,7 @@ static TensorMapEncodeFn tensor_map_encoder() {
 }
 // 2-D map over `planes` stacked n x n planes of `csz`-byte complex samples, seen as FP32 words:
 // dim0 = n * csz / 4 words (one grid row), dim1 = planes * n rows; box = w columns x `box_rows` rows
-static bool encode_plane_map(CUtensorMap* tm, void* base, int n, long long planes, int csz, int w, int box_rows) {
+static bool encode_plane_map(CUtensorMap* tm, void* base, int n, long long planes, int csz, int w, int box_rows, bool swizzle64 = false) {
     TensorMapEncodeFn enc = tensor_map_encoder();
     if (enc == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)n * (cuuint64_t)(csz / 4), (cuuint64_t)planes * (cuuint64_t)n};
@@ -44,7 +44,8 @@ static bool encode_plane_map(CUtensorMap* tm, void* base, int n, long long plane
     const cuuint32_t box[2] = {(cuuint32_t)(w * csz / 4), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static thread_local std::string t_err;
@@ -119,6 +120,7 @@ struct lp2d_plan {
     const Q4Ops<double>* q4_64;
     int q4_ctas;               // resident CTAs per SM (1)
     int q4_lag;                // tuning override (0 = automatic)
+    int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
     int p2_ctas_factor, p2_ctas_plain;
     void* p2_tw;               // twiddles of the P2 (N, E) schedule
@@ -259,7 +261,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         if (host_a[k] != host_a[n - k] || host_b[k] != host_b[n - k]) p->h_even = false;
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
-    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0;
+    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -324,6 +326,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
                 p->q4_ops = env ? atoi(env) : q4_default;
             }
             env = getenv("LP2D_Q4_LAG"); p->q4_lag = env ? atoi(env) : 0;
+            env = getenv("LP2D_Q4_COLPRIV"); p->q4_colpriv = env ? atoi(env) : 0;
         }
     }
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
@@ -525,7 +528,17 @@ int run_q4(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.hints = hints;
         a.use_tma = 1;
         const int box_rows = p->n < 256 ? p->n : 256;
-        if (!encode_plane_map(&a.tm_ring, p->ring, p->n, (long long)slots, (int)sizeof(cx<T>), ops->w, box_rows))
+        // warp-private final column stage (pipe3.cuh): one warp per column, swizzled tile, results leave by a TMA store.
+        // Two-stage steps whose last stage only writes the complex plane; a tile row must be 64 bytes, a line one warp.
+        const bool col_private = p->q4_colpriv && nstages == 2 && !a.st[1].mid && a.st[1].out != nullptr && a.st[1].inten == nullptr &&
+                                 ops->w * (int)sizeof(cx<T>) == 64 && p->n / ops->e == 32 && ops->threads - 64 == 32 * ops->w &&
+                                 (reinterpret_cast<uintptr_t>(a.st[1].out) & 15) == 0;
+        if (col_private) {
+            if (!encode_plane_map(&a.tm_out, a.st[1].out, p->n, nb, (int)sizeof(cx<T>), ops->w, box_rows, true))
+                return fail(LP2D_ECUDA, "fused step: cuTensorMapEncodeTiled (output) failed");
+            a.use_tma = 2;
+        }
+        if (!encode_plane_map(&a.tm_ring, p->ring, p->n, (long long)slots, (int)sizeof(cx<T>), ops->w, box_rows, col_private))
             return fail(LP2D_ECUDA, "fused step: cuTensorMapEncodeTiled failed");
         const long long total = ((long long)a.ngroups + (long long)(nstages - 1) * lag) * nstages * tiles;
         if (total > 0x7fffffffll) return fail(LP2D_EINVAL, "fused step: batch too large for one launch");

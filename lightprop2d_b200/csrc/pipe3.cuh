@@ -232,6 +232,35 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
     }
 }
 
+// Warp-private form of the FINAL column stage (use_tma == 2): the tile lands with the TMA unit's 64-byte swizzle
+// (16-byte chunk index ^= (row >> 1) & 3), which spreads the rows of one column over the banks well enough (two-way
+// instead of eight-way conflicts) for ONE WARP to own a column: no exchange between warps, hence no CTA-wide barrier in
+// the item, and the warps of the CTA are free to drift apart -- one can be in its load/store phase while another is in
+// its floating-point phase.  The results go back to the same (swizzled) slots of the landing buffer and leave through a
+// TMA tensor store issued by the signaller thread, which hands the buffer back when the store has read it.
+template <typename T, int N, int E, int W, int NBUF, bool INV>
+__device__ __forceinline__ void q4_col_private_item(const P2Args<T>& p, unsigned char* land, cx<T>* xbuf, const cx<T>* __restrict__ stw,
+                                                    int ctid) {
+    using K = Q4Cfg<T, N, E, W, NBUF>;
+    constexpr int TPL = K::TPL;
+    static_assert(TPL == 32 && W * K::SZ == 64 && K::NCW == W, "one warp per column, 64-byte tile rows");
+    const int w = ctid >> 5, t = ctid & 31;
+    const int cw = (w * K::SZ) ^ (((t >> 1) & 3) << 4);                    // swizzled byte offset of column w in rows t + 32 m
+    cx<T> v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = *reinterpret_cast<const cx<T>*>(land + (t + TPL * m) * 64 + cw);
+    line_fft<T, N, E, SYNC_WARP, 0, true>(v, xbuf + w * K::LS, stw, t, w);
+    const T scale = p.st[1].scale;
+    const int r0 = INV ? ((N - t) & (N - 1)) : t;                          // output row of v[0]; v[m]: r0 -/+ 32 m (mod N)
+    const int co = (w * K::SZ) ^ (((r0 >> 1) & 3) << 4);                   // (32 m never changes bits 1..2 of the row)
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int row = INV ? ((N - t - TPL * m) & (N - 1)) : t + TPL * m;
+        *reinterpret_cast<cx<T>*>(land + row * 64 + co) = cscale(v[m], scale);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> the TMA store
+}
+
 template <typename T, int N, int E, int W, int NBUF, int HOOKS>
 __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel(const __grid_constant__ P2Args<T> p) {
     using K = Q4Cfg<T, N, E, W, NBUF>;
@@ -329,6 +358,19 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
                 if (item < 0) break;
                 P2Item it;
                 p2_decode<T, K::TILES>(p, item, it);
+                if (p.use_tma == 2 && it.s == 1) {
+                    // warp-private column item: its results are staged in the landing buffer; store the tile, and hand
+                    // the buffer back to the producer once the store has read it
+                    const int buf = (int)(k % Q4_NBUF);
+                    unsigned char* land = smem + (size_t)buf * K::TILE_BYTES;
+                    constexpr int FPC = K::SZ / 4;
+#pragma unroll
+                    for (int q = 0; q < N / K::BOX; ++q)
+                        p2_tma_store_2d(&p.tm_out, it.tile * W * FPC, it.g * N + q * K::BOX, land + (size_t)q * K::BOX * W * K::SZ);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(p2_smem_u32(&s_empty[buf])), "r"(K::NCW) : "memory");
+                }
                 unsigned int* ctr = p.counters + 1 + it.s * p.ngroups + it.g;
                 if (it.s == p.nstages - 1) p2_signal_consumed(ctr);
                 else p2_signal(ctr);
@@ -353,13 +395,23 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
                 if (p.st[0].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
                 else q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, land, xbuf, stw, eb, tid, after_col);
             } else if (it.s == 1) {
+                if constexpr (K::TPL == 32 && W * K::SZ == 64 && K::NCW == W) {
+                    if (p.use_tma == 2) {
+                        unsigned char* lb = smem + (size_t)buf * K::TILE_BYTES;
+                        if (p.st[1].inverse) q4_col_private_item<T, N, E, W, NBUF, true>(p, lb, xbuf, stw, tid);
+                        else q4_col_private_item<T, N, E, W, NBUF, false>(p, lb, xbuf, stw, tid);
+                        goto item_done;
+                    }
+                }
                 if (p.st[1].mid) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, true, true, false>(p, it, land, xbuf, stw, eb, tid, after_col);
                 else if (p.st[1].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
                 else q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, false>(p, it, land, xbuf, stw, eb, tid, after_col);
             } else {
                 q4_item<T, N, E, W, NBUF, HOOKS, 2, AX_ROW, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
             }
-            after_col = (it.s == 1);
+        item_done:
+            // (warp-private column mode: the exchange regions are private to a warp in row AND column items)
+            after_col = (it.s == 1) && p.use_tma != 2;
         }
         __syncwarp();                                      // the warp's stores of the item are issued
         if ((tid & 31) == 0) q4_mbar_arrive(&s_done[k % Q4_NDONE]);

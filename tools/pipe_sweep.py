@@ -45,7 +45,7 @@ def main():
     print(f"n={n} bits={bits} batch={batch}; us/beam (fraction of {hbm/1e9:.0f} GB/s on algorithmic bytes)")
     print(" ".join(f"{k:>6s}" for k in keys) + " | fft2(2PB) | stateful(3PB) | fresh f->f(2PB)")
     envname = {"G": "LP2D_PIPE_G", "LAG": "LP2D_PIPE_LAG", "SLOTS": "LP2D_PIPE_SLOTS", 
-               "RING": "LP2D_RING_MB", "PIPE": "LP2D_PIPE", "VAR": "LP2D_PIPE_VARIANT", "HINTS": "LP2D_PIPE_HINTS", "PERSIST": "LP2D_PIPE_PERSIST", "OPS": "LP2D_FUSED_OPS", "TMA": "LP2D_TMA", "FORM": "LP2D_PIPE_FORM", "QLAG": "LP2D_Q4_LAG", "QVAR": "LP2D_Q4_VARIANT"}
+               "RING": "LP2D_RING_MB", "PIPE": "LP2D_PIPE", "VAR": "LP2D_PIPE_VARIANT", "HINTS": "LP2D_PIPE_HINTS", "PERSIST": "LP2D_PIPE_PERSIST", "OPS": "LP2D_FUSED_OPS", "TMA": "LP2D_TMA", "FORM": "LP2D_PIPE_FORM", "QLAG": "LP2D_Q4_LAG", "QVAR": "LP2D_Q4_VARIANT", "CP": "LP2D_Q4_COLPRIV"}
     for combo in itertools.product(*vals):
         for k, v in zip(keys, combo):
             os.environ[envname[k]] = v
