@@ -262,6 +262,11 @@ LP2D_API int lp2d_resample(int dtype, const void* in, long long in_plane, int ld
  * receives a short description (at most name_len - 1 characters). */
 LP2D_API int lp2d_plan_step_kernel(lp2d_plan* plan, char* name, int name_len);
 
+/* Tuning aid: with LP2D_Q4_TIMING=1 in the environment when the plan is created, the persistent step kernel sums the
+ * clock ticks its transform warps spend per phase; host16 receives [row items: wait, tile -> registers, factor,
+ * transform + stores, item count, 0, 0, 0 | column items: the same].  LP2D_EINVAL when not enabled. */
+LP2D_API int lp2d_q4_timing(lp2d_plan* plan, unsigned long long* host16, int reset);
+
 /* How many kernels this library has launched in this process (for bench accounting). */
 LP2D_API long long lp2d_launch_count(void);
 

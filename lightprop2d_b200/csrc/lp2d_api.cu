@@ -120,6 +120,7 @@ struct lp2d_plan {
     const Q4Ops<double>* q4_64;
     int q4_ctas;               // resident CTAs per SM (1)
     int q4_lag;                // tuning override (0 = automatic)
+    unsigned long long* q4_timing;   // tuning aid: phase clocks of the persistent form (LP2D_Q4_TIMING=1), else NULL
     int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
     int p2_ctas_factor, p2_ctas_plain;
@@ -261,7 +262,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         if (host_a[k] != host_a[n - k] || host_b[k] != host_b[n - k]) p->h_even = false;
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
-    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0;
+    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -327,6 +328,9 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             }
             env = getenv("LP2D_Q4_LAG"); p->q4_lag = env ? atoi(env) : 0;
             env = getenv("LP2D_Q4_COLPRIV"); p->q4_colpriv = env ? atoi(env) : 0;
+            env = getenv("LP2D_Q4_TIMING");
+            if (env && atoi(env) != 0 && cudaMalloc(&p->q4_timing, 16 * sizeof(unsigned long long)) == cudaSuccess)
+                cudaMemset(p->q4_timing, 0, 16 * sizeof(unsigned long long));
         }
     }
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
@@ -390,8 +394,16 @@ int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
     return fused ? 1 : 0;
 }
 
+int lp2d_q4_timing(lp2d_plan* p, unsigned long long* host16, int reset) {
+    if (p == nullptr || p->q4_timing == nullptr || host16 == nullptr) return fail(LP2D_EINVAL, "q4_timing: not enabled (LP2D_Q4_TIMING=1)");
+    cudaError_t e = cudaMemcpy(host16, p->q4_timing, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && reset) e = cudaMemset(p->q4_timing, 0, 16 * sizeof(unsigned long long));
+    return e == cudaSuccess ? LP2D_OK : cuda_fail(e, "q4_timing");
+}
+
 int lp2d_plan_destroy(lp2d_plan* p) {
     if (p == nullptr) return LP2D_OK;
+    cudaFree(p->q4_timing);
     cudaFree(p->tw);
     cudaFree(p->tabs);
     cudaFree(p->ring);
@@ -526,6 +538,7 @@ int run_q4(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.fac_map = fac_kind == P2_FAC_LENS ? (p->x2_even ? P2_MAP_CENTRE : P2_MAP_FULL) : P2_MAP_FREQ;
         a.fac_stride = (fac_kind == P2_FAC_LENS && !p->x2_even) ? p->n : ops->fl;
         a.hints = hints;
+        a.timing = p->q4_timing;
         a.use_tma = 1;
         const int box_rows = p->n < 256 ? p->n : 256;
         // warp-private final column stage (pipe3.cuh): one warp per column, swizzled tile, results leave by a TMA store.

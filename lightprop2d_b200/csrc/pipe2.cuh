@@ -75,6 +75,9 @@ struct P2Args {
     // TMA path of the final column stage of two-stage steps (use_tma != 0): 2-D tensor maps over the ring
     // and over the output planes, seen as [plane * N + row][N * sizeof(complex) / 4 floats]
     int use_tma;
+    // tuning aid (persistent form): per item kind (row / column) x phase, summed clock64 ticks of lane 0 of every
+    // transform warp + item counts; NULL in production (LP2D_Q4_TIMING=1 allocates it, lp2d_q4_timing reads it)
+    unsigned long long* timing;
     alignas(64) CUtensorMap tm_ring;
     alignas(64) CUtensorMap tm_out;
 };

@@ -128,7 +128,8 @@ __device__ __forceinline__ void q4_wait_ready(const P2Args<T>& p, int item, unsi
 // One item on the consumer threads.  `land` holds the tile: rows as [line][N] (dense), columns as [row][W].
 template <typename T, int N, int E, int W, int NBUF, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
 __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, const cx<T>* __restrict__ land, cx<T>* xbuf,
-                                        const cx<T>* __restrict__ stw, uint64_t* empty_bar, int ctid, bool after_column_item) {
+                                        const cx<T>* __restrict__ stw, uint64_t* empty_bar, int ctid, bool after_column_item,
+                                        long long* tmark) {
     using K = Q4Cfg<T, N, E, W, NBUF>;
     constexpr int TPL = K::TPL;
     constexpr long long PLANE = (long long)N * N;
@@ -154,6 +155,7 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
     if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
+    if (tmark) tmark[1] = clock64();                       // tile in registers
     if constexpr (!IN_RING) {
         if (st.mask_kind != MASK_NONE) {
             const long long mb = b * st.mask_beam_stride + off0;
@@ -169,6 +171,7 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
             }
         }
     }
+    if (tmark) tmark[2] = clock64();                       // pointwise factor applied
     // The global stores ride on the butterflies (hooks of dft_reg): the state (spectrum * H, field * lens ...) goes out
     // while the first radix pass consumes it, the result while the last radix pass produces it.
     cx<T>* const pre_dst = (!IN_RING && st.out_pre != nullptr) ? st.out_pre + b * PLANE + off0 + t * PSTRIDE : nullptr;
@@ -384,7 +387,11 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
     bool after_col = false;
     for (unsigned int k = 0;; ++k) {
         const int buf = (int)(k % Q4_NBUF);
+        long long tmarks[4];
+        long long* tm = (p.timing != nullptr) ? tmarks : nullptr;
+        if (tm) tm[0] = clock64();
         p2_mbar_wait(&s_full[buf], (k / Q4_NBUF) & 1u);
+        if (tm) { tm[3] = clock64(); tm[1] = tm[2] = tm[3]; }
         const int item = s_desc[buf];
         if (item >= 0) {
             P2Item it;
@@ -392,8 +399,8 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
             const cx<T>* land = reinterpret_cast<const cx<T>*>(smem + (size_t)buf * K::TILE_BYTES);
             uint64_t* eb = &s_empty[buf];
             if (it.s == 0) {
-                if (p.st[0].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
-                else q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, land, xbuf, stw, eb, tid, after_col);
+                if (p.st[0].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, true>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
+                else q4_item<T, N, E, W, NBUF, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
             } else if (it.s == 1) {
                 if constexpr (K::TPL == 32 && W * K::SZ == 64 && K::NCW == W) {
                     if (p.use_tma == 2) {
@@ -403,17 +410,29 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
                         goto item_done;
                     }
                 }
-                if (p.st[1].mid) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, true, true, false>(p, it, land, xbuf, stw, eb, tid, after_col);
-                else if (p.st[1].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
-                else q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, false>(p, it, land, xbuf, stw, eb, tid, after_col);
+                if (p.st[1].mid) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, true, true, false>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
+                else if (p.st[1].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
+                else q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, false>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
             } else {
-                q4_item<T, N, E, W, NBUF, HOOKS, 2, AX_ROW, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col);
+                q4_item<T, N, E, W, NBUF, HOOKS, 2, AX_ROW, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
             }
         item_done:
             // (warp-private column mode: the exchange regions are private to a warp in row AND column items)
             after_col = (it.s == 1) && p.use_tma != 2;
         }
         __syncwarp();                                      // the warp's stores of the item are issued
+        if (tm && item >= 0 && (tid & 31) == 0) {
+            // bins: [kind][0] wait for the tile, [1] tile -> registers, [2] factor, [3] transform + stores, [4] items
+            P2Item it2;
+            p2_decode<T, K::TILES>(p, item, it2);
+            unsigned long long* bin = p.timing + (p.st[it2.s].axis == AX_ROW ? 0 : 8);
+            const long long tend = clock64();
+            atomicAdd(&bin[0], (unsigned long long)(tm[3] - tm[0]));
+            atomicAdd(&bin[1], (unsigned long long)(tm[1] - tm[3]));
+            atomicAdd(&bin[2], (unsigned long long)(tm[2] - tm[1]));
+            atomicAdd(&bin[3], (unsigned long long)(tend - tm[2]));
+            atomicAdd(&bin[4], 1ull);
+        }
         if ((tid & 31) == 0) q4_mbar_arrive(&s_done[k % Q4_NDONE]);
         if (item < 0) break;
     }
