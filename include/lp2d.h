@@ -262,7 +262,21 @@ LP2D_API int lp2d_resample(int dtype, const void* in, long long in_plane, int ld
  * receives a short description (at most name_len - 1 characters). */
 LP2D_API int lp2d_plan_step_kernel(lp2d_plan* plan, char* name, int name_len);
 
-/* Tuning aid: with LP2D_Q4_TIMING=1 in the environment when the plan is created, the persistent step kernel sums the
+/* Spectrum layout of a plan.  transposed = 1: every SPECTRUM buffer the 2-D calls of this plan read or write
+ * (lp2d_fft2 output / inverse input, lp2d_propagate / _sweep state, lp2d_lens output, lp2d_mul_fft2 forward output /
+ * inverse data, lp2d_propagate_field spectrum_out) is stored transposed: memory row j holds grid column j of the
+ * spectrum the reference keeps (Beam2D.spectrum[i, j], beam2d.py:130-133).  Fields, masks of fields and intensities
+ * keep their natural orientation; a mask applied to a spectrum (lp2d_mul_fft2 with inverse = 1) must be given
+ * transposed too.  Why: the final column stage of a 2-D transform then stores whole rows of the destination
+ * instead of 64-byte pieces one row apart, and every HBM access of a step is a contiguous row.
+ * Only where the fused step kernel exists (LP2D_EUNSUPPORTED otherwise); calls that cannot take the fused path on
+ * such a plan fail with LP2D_EUNSUPPORTED instead of silently using another layout.  lp2d_transpose converts. */
+LP2D_API int lp2d_plan_set_spectrum_layout(lp2d_plan* plan, int transposed);
+LP2D_API int lp2d_plan_get_spectrum_layout(lp2d_plan* plan);
+/* out[b][j][i] = in[b][i][j] for `batch` planes of n x n complex samples (in != out). */
+LP2D_API int lp2d_transpose(int dtype, const void* in, void* out, int n, long long batch, void* stream);
+
+/* Tuning aid (builds with LP2D_BUILD_DEFS="-DLP2D_Q4_CLOCKS=1" only): with LP2D_Q4_TIMING=1 in the environment when the plan is created, the persistent step kernel sums the
  * clock ticks its transform warps spend per phase; host16 receives [row items: wait, tile -> registers, factor,
  * transform + stores, item count, 0, 0, 0 | column items: the same].  LP2D_EINVAL when not enabled. */
 LP2D_API int lp2d_q4_timing(lp2d_plan* plan, unsigned long long* host16, int reset);

@@ -58,6 +58,9 @@ SIGNATURES = {
     "lp2d_resample": (_i, [_i, _vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
     "lp2d_plan_step_kernel": (_i, [_vp, C.c_char_p, _i]),
     "lp2d_q4_timing": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
+    "lp2d_plan_set_spectrum_layout": (_i, [_vp, _i]),
+    "lp2d_plan_get_spectrum_layout": (_i, [_vp]),
+    "lp2d_transpose": (_i, [_i, _vp, _vp, _i, _ll, _vp]),
     "lp2d_launch_count": (_ll, []),
 }
 

@@ -25,6 +25,7 @@ Differences a caller can see (all documented in DESIGN.md):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections.abc import Iterable
 from dataclasses import dataclass
 from typing import Tuple
@@ -56,12 +57,14 @@ def _dptr(a: np.ndarray):
 class _Plan:
     """Owner of one lp2d_plan (twiddles + FP64 grid tables on one device)."""
 
-    def __init__(self, n, bits, a_tab, b_tab, x2_tab):
+    def __init__(self, n, bits, a_tab, b_tab, x2_tab, spectrum_t=False):
         lib = _lib.load()
         self.handle = C.c_void_p()
         a_tab, b_tab, x2_tab = (np.ascontiguousarray(v, dtype=np.float64) for v in (a_tab, b_tab, x2_tab))
         _lib.check(lib.lp2d_plan_create(C.byref(self.handle), int(n), _lib.C64 if bits == 64 else _lib.C128,
                                         _dptr(a_tab), _dptr(b_tab), _dptr(x2_tab)), "plan_create")
+        # transposed spectrum layout (include/lp2d.h): taken where the library offers it, natural layout otherwise
+        self.spectrum_t = bool(spectrum_t) and lib.lp2d_plan_set_spectrum_layout(self.handle, 1) == 0
 
     def __del__(self):
         try:
@@ -71,16 +74,16 @@ class _Plan:
             pass
 
 
-def _get_plan(device_index, n, bits, area_size, wl, a_tab, b_tab, x2_tab):
+def _get_plan(device_index, n, bits, area_size, wl, a_tab, b_tab, x2_tab, spectrum_t=False):
     # X may have been shifted in place by a generator (reference quirk), so x2 is part of the key
-    key = (device_index, n, bits, float(area_size), float(wl), x2_tab.tobytes())
+    key = (device_index, n, bits, float(area_size), float(wl), x2_tab.tobytes(), bool(spectrum_t))
     p = _PLAN_CACHE.get(key)
     if p is None:
         if len(_PLAN_CACHE) > 16:
             _PLAN_CACHE.clear()
         torch = _torch()
         with torch.cuda.device(device_index):
-            p = _Plan(n, bits, a_tab, b_tab, x2_tab)
+            p = _Plan(n, bits, a_tab, b_tab, x2_tab, spectrum_t)
         _PLAN_CACHE[key] = p
     return p
 
@@ -135,8 +138,8 @@ class Beam2D:
                 "'init_field_gen' must be a function or 'init_field' must be an array.")
         self._f = self._asdev(field, self.complex)
         self._check_shape(self._f)
-        self._s = None if self.init_spectrum is None else self._asdev(self.init_spectrum, self.complex)
         self._new_plan()
+        self._s = None if self.init_spectrum is None else self._ingest_spectrum(self.init_spectrum)
 
     def _construct_grids(self):
         """Grids with the reference's expressions (beam2d.py:299-308); host numpy float64."""
@@ -168,7 +171,10 @@ class Beam2D:
         dt = _lib.C64 if self.complex_bits == 64 else _lib.C128
         pow2 = n >= 1 and (n & (n - 1)) == 0
         if pow2 and int(self._lib.lp2d_min_npoints()) <= n <= int(self._lib.lp2d_max_npoints(dt)):
-            self._plan = _get_plan(int(self.device), n, self.complex_bits, self.area_size, self.wl, a_tab, b_tab, x2_tab)
+            # LP2D_SPECTRUM_T=1: the spectrum state is kept transposed on the device (every HBM access of a fused step
+            # is then a contiguous row); `spectrum` is converted on access, so callers see the reference's orientation
+            self._plan = _get_plan(int(self.device), n, self.complex_bits, self.area_size, self.wl, a_tab, b_tab, x2_tab,
+                                   os.environ.get("LP2D_SPECTRUM_T", "0") == "1")
             self._gen = None
         else:
             # any other npoints / grids above lp2d_max_npoints: pointwise kernels + a generic 2-D DFT engine
@@ -248,13 +254,31 @@ class Beam2D:
         self._f = self._asdev(value, self.complex)
 
     @property
+    def _st(self):
+        """True when the spectrum state ``_s`` is held transposed (plan with the transposed spectrum layout)."""
+        return self._plan is not None and self._plan.spectrum_t
+
+    def _transposed(self, t):
+        out = _torch().empty_like(t)
+        n = int(self.npoints)
+        self._call("lp2d_transpose", _lib.C64 if self.complex_bits == 64 else _lib.C128, t.data_ptr(), out.data_ptr(),
+                   n, t.numel() // (n * n), self._stream())
+        return out
+
+    def _ingest_spectrum(self, value):
+        """A spectrum in the reference's orientation -> the state ``_s`` in the plan's layout."""
+        t = self._asdev(value, self.complex)
+        self._check_shape(t)
+        return self._transposed(t) if self._st else t
+
+    @property
     def spectrum(self):
         self._materialise_spectrum()
-        return self._expose(self._s)
+        return self._expose(self._transposed(self._s) if self._st else self._s)
 
     @spectrum.setter
     def spectrum(self, value):
-        self._s = self._asdev(value, self.complex)
+        self._s = self._ingest_spectrum(value)
 
     def _materialise_spectrum(self):
         if self._s is None:
@@ -273,7 +297,7 @@ class Beam2D:
         if self._f.dtype != self._cdtype:
             self._f = self._f.to(self._cdtype)
         self._check_shape(self._f)
-        self._s = None if spectrum is None else self._asdev(spectrum, self.complex)
+        self._s = None if spectrum is None else self._ingest_spectrum(spectrum)
 
     # ------------------------------------------------------------------ hot path
     def propagate(self, z: float):
@@ -405,6 +429,8 @@ class Beam2D:
                 mt, kind, stride, ptr = None, 0, 0, None
             else:
                 mt, kind, stride = self._mask_to_device(mask)
+                if spectral and self._st:                  # the spectrum is held transposed: so must its mask be
+                    mt = mt.transpose(-1, -2).contiguous()
                 ptr = mt.data_ptr()
             self._call("lp2d_mul_fft2", self._plan.handle, data.data_ptr(), other.data_ptr(), ptr, kind,
                        stride, self._batch(), 1 if spectral else 0, self._stream())

@@ -19,6 +19,8 @@ LIB = os.path.join(HERE, "liblp2d.so")
 UNITS = ["lp2d_api.cu", "lp2d_aux.cu", "lp2d_f32.cu", "lp2d_f64.cu", "lp2d_p2_f32.cu", "lp2d_p2_f64.cu", "lp2d_modes_tc.cu", "lp2d_xl.cu", "lp2d_generic.cu"]
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+# tuning builds only: extra -D definitions (LP2D_Q4_CLOCKS=1 phase clocks, LP2D_ABLATION=1 no-transform variants)
+NVCC_FLAGS += os.environ.get("LP2D_BUILD_DEFS", "").split()
 
 
 def _nvcc():

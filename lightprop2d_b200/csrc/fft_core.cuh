@@ -188,9 +188,8 @@ struct LinePlan {
 };
 
 // How the TPL threads of one line synchronise around a shared-memory exchange.
-// SYNC_CONSUMERS: the transform threads of a warp-specialised CTA (pipe3.cuh) without its helper warps
-enum { SYNC_WARP = 0, SYNC_NAMED = 1, SYNC_CTA = 2, SYNC_CONSUMERS = 3 };
-#define LP2D_Q4_CONSUMER_THREADS 256
+// SYNC_CONSUMERS + n: the n transform threads of a warp-specialised CTA (pipe3.cuh) without its helper warps
+enum { SYNC_WARP = 0, SYNC_NAMED = 1, SYNC_CTA = 2, SYNC_CONSUMERS = 4096 };
 
 template <int MODE, int TPL>
 __device__ __forceinline__ void line_sync(int line_in_cta) {
@@ -198,8 +197,8 @@ __device__ __forceinline__ void line_sync(int line_in_cta) {
         __syncwarp();
     } else if (MODE == SYNC_NAMED) {
         asm volatile("bar.sync %0, %1;" ::"r"(line_in_cta + 1), "r"(TPL) : "memory");
-    } else if (MODE == SYNC_CONSUMERS) {
-        asm volatile("bar.sync 15, %0;" ::"n"(LP2D_Q4_CONSUMER_THREADS) : "memory");
+    } else if (MODE >= SYNC_CONSUMERS) {
+        asm volatile("bar.sync 15, %0;" ::"n"(MODE - SYNC_CONSUMERS) : "memory");
     } else {
         __syncthreads();
     }
@@ -315,6 +314,19 @@ __device__ __forceinline__ void line_fft(cx<T> (&v)[E], cx<T>* sline, const cx<T
     line_pass<T, N, E, P, SYNC, TWS, PRE, POST>(v, sline, tw, t, line_in_cta, pre, post);
     if constexpr (P + 1 < LinePlan<N, E>::npass())
         line_fft<T, N, E, SYNC, P + 1, TWS, PRE, POST>(v, sline, tw, t, line_in_cta, pre, post);
+}
+
+// line_fft for a transform whose threads change lines at the first exchange: pass 0 runs with the ownership of the
+// load (sline0, t0, l0), the passes after it with (sline1, t1, l1).  Column tiles are read with consecutive threads on
+// consecutive columns of a grid row (coalesced pieces of a row); when the result is stored TRANSPOSED, a warp should own
+// one line instead, so that its stores are whole 256-byte runs of the destination row.  SYNC must cover every thread
+// of the tile (SYNC_CTA / SYNC_CONSUMERS).
+template <typename T, int N, int E, int SYNC, bool TWS = false, typename POST = NoHook>
+__device__ __forceinline__ void line_fft_remap(cx<T> (&v)[E], cx<T>* sline0, int t0, int l0, cx<T>* sline1, int t1, int l1,
+                                               const cx<T>* tw, POST post = POST()) {
+    static_assert(LinePlan<N, E>::npass() >= 2, "needs an exchange");
+    line_pass<T, N, E, 0, SYNC, TWS, NoHook, POST>(v, sline0, tw, t0, l0, NoHook(), post);
+    line_fft<T, N, E, SYNC, 1, TWS, NoHook, POST>(v, sline1, tw, t1, l1, NoHook(), post);
 }
 
 }  // namespace lp2d

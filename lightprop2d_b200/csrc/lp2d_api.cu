@@ -121,6 +121,7 @@ struct lp2d_plan {
     int q4_ctas;               // resident CTAs per SM (1)
     int q4_lag;                // tuning override (0 = automatic)
     unsigned long long* q4_timing;   // tuning aid: phase clocks of the persistent form (LP2D_Q4_TIMING=1), else NULL
+    int spectrum_t;            // spectra of this plan are stored TRANSPOSED (lp2d_plan_set_spectrum_layout)
     int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
     int p2_ctas_factor, p2_ctas_plain;
@@ -262,7 +263,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
         if (host_a[k] != host_a[n - k] || host_b[k] != host_b[n - k]) p->h_even = false;
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
-    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr;
+    p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr; p->spectrum_t = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -393,6 +394,19 @@ int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
     }
     return fused ? 1 : 0;
 }
+
+int lp2d_plan_set_spectrum_layout(lp2d_plan* p, int transposed) {
+    if (p == nullptr) return fail(LP2D_EINVAL, "set_spectrum_layout: NULL plan");
+    if (transposed) {
+        if ((p->p2_32 == nullptr && p->p2_64 == nullptr) || !p->h_even)
+            return fail(LP2D_EUNSUPPORTED, "set_spectrum_layout: the transposed layout needs the fused step kernel (no instance for this size / tables)");
+        // every two-stage step must fit the ring with its default schedule; run_p2 reports it per call otherwise
+    }
+    p->spectrum_t = transposed ? 1 : 0;
+    return LP2D_OK;
+}
+
+int lp2d_plan_get_spectrum_layout(lp2d_plan* p) { return p != nullptr ? p->spectrum_t : 0; }
 
 int lp2d_q4_timing(lp2d_plan* p, unsigned long long* host16, int reset) {
     if (p == nullptr || p->q4_timing == nullptr || host16 == nullptr) return fail(LP2D_EINVAL, "q4_timing: not enabled (LP2D_Q4_TIMING=1)");
@@ -543,7 +557,7 @@ int run_q4(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         const int box_rows = p->n < 256 ? p->n : 256;
         // warp-private final column stage (pipe3.cuh): one warp per column, swizzled tile, results leave by a TMA store.
         // Two-stage steps whose last stage only writes the complex plane; a tile row must be 64 bytes, a line one warp.
-        const bool col_private = p->q4_colpriv && nstages == 2 && !a.st[1].mid && a.st[1].out != nullptr && a.st[1].inten == nullptr &&
+        const bool col_private = p->q4_colpriv && nstages == 2 && !a.st[1].mid && !a.st[1].out_t && a.st[1].out != nullptr && a.st[1].inten == nullptr &&
                                  ops->w * (int)sizeof(cx<T>) == 64 && p->n / ops->e == 32 && ops->threads - 64 == 32 * ops->w &&
                                  (reinterpret_cast<uintptr_t>(a.st[1].out) & 15) == 0;
         if (col_private) {
@@ -644,7 +658,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.fac_stride = (fac_kind == P2_FAC_LENS && !p->x2_even) ? p->n : ops->fl;
         a.hints = p->pipe_hints >= 0 ? p->pipe_hints : (P2_HINT_KEEP_RING | 1 | (nstages == 2 ? P2_HINT_PREFETCH : 0));
         a.use_tma = 0;
-        if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && a.st[1].out != nullptr &&
+        if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && !a.st[1].out_t && a.st[1].out != nullptr &&
             (ops->w * (int)sizeof(cx<T>)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.st[1].out) & 15) == 0) {
             const int box_rows = p->n < 256 ? p->n : 256;
             if (encode_plane_map(&a.tm_ring, p->ring, p->n, (long long)slots * G, (int)sizeof(cx<T>), ops->w, box_rows) &&
@@ -761,8 +775,11 @@ int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const v
         if (mask != nullptr) { st[0].mask = mask; st[0].mask_kind = mask_kind; st[0].mask_beam_stride = mask_stride; }
         st[1].in_ring = 1;
         st[1].out = static_cast<cx<T>*>(other);
-        const int rc = (p->fused_ops & (state_out != nullptr ? 2 : 1)) ? run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s, state_out != nullptr ? 2 : 1) : -1;
+        st[1].out_t = p->spectrum_t;
+        const int rc = (p->spectrum_t || (p->fused_ops & (state_out != nullptr ? 2 : 1)))
+                           ? run_p2<T>(p, st, 2, st[0].pre, 0, k0, two_f, batch, s, state_out != nullptr ? 2 : 1) : -1;
         if (rc >= 0) return rc;
+        if (p->spectrum_t) return fail(LP2D_EUNSUPPORTED, "transposed spectrum layout: the fused step kernel does not apply to this call");
     }
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
@@ -811,8 +828,12 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         st[1].in_ring = 1;
         st[1].out = static_cast<cx<T>*>(field);
         st[1].inten = static_cast<T*>(intensity);
-        const int rc = (p->fused_ops & 2) ? run_p2<T>(p, st, 2, P2_FAC_H, 0, z, 0.0, batch, s, 2) : -1;
+        // transposed spectrum: a memory row is a grid COLUMN of the spectrum (factor rows by column), and the column
+        // stage's transposed store lands the field in its natural orientation
+        st[1].out_t = p->spectrum_t;
+        const int rc = (p->spectrum_t || (p->fused_ops & 2)) ? run_p2<T>(p, st, 2, P2_FAC_H, p->spectrum_t, z, 0.0, batch, s, 2) : -1;
         if (rc >= 0) return rc;
+        if (p->spectrum_t) return fail(LP2D_EUNSUPPORTED, "transposed spectrum layout: the fused step kernel does not apply to this call");
     }
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
@@ -845,6 +866,13 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
 template <typename T>
 int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, void* intensity, void* work,
                     long long work_bytes, long long batch, double z, cudaStream_t s) {
+    if (p->spectrum_t && spec_out != nullptr) {
+        // transposed spectrum wanted as a by-product: fft2 (-> transposed spectrum), then the stateful step
+        if (fout == nullptr) return fail(LP2D_EUNSUPPORTED, "propagate_field: transposed spectrum_out needs field_out");
+        int rc = mul_fft2<T>(p, fin, nullptr, spec_out, nullptr, 0, 0, batch, 0, PRE_NONE, 0, 0, s);
+        if (rc) return rc;
+        return propagate_state<T>(p, spec_out, fout, intensity, batch, z, s);
+    }
     {
         // forward rows -> ring; columns: FFT, H, inverse FFT in the ring; inverse rows -> field / |E|^2
         const T inv_n = (T)(1.0 / (double)p->n);

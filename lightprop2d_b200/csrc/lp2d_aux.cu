@@ -51,6 +51,28 @@ __global__ void pack_transpose_kernel(const cx<T>* __restrict__ in, cx<T>* __res
     }
 }
 
+// out[b][c][r] = in[b][r][c], n x n planes: 32 x 32 samples per CTA through padded shared memory (conversion between
+// the natural and the transposed spectrum layout; not on the step path)
+template <typename T>
+__global__ void transpose_kernel(const cx<T>* __restrict__ in, cx<T>* __restrict__ out, int n, long long batch) {
+    __shared__ cx<T> s[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (long long b = blockIdx.z; b < batch; b += gridDim.z) {
+        const cx<T>* src = in + b * (long long)n * n;
+        cx<T>* dst = out + b * (long long)n * n;
+        for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+            const int r = r0 + k, c = c0 + threadIdx.x;
+            if (r < n && c < n) s[k][threadIdx.x] = src[(long long)r * n + c];
+        }
+        __syncthreads();
+        for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+            const int c = c0 + k, r = r0 + threadIdx.x;
+            if (r < n && c < n) dst[(long long)c * n + r] = s[threadIdx.x][k];
+        }
+        __syncthreads();
+    }
+}
+
 // Counter-based RNG (Philox4x32-10, Salmon et al. 2011) for ensembles generated on the device: the four
 // words of block `ctr` of beam `beam` depend only on (seed, beam, ctr), so a beam is the same whatever the
 // batch / shard it is generated in.
@@ -353,6 +375,20 @@ int lp2d_pack_transpose(int dtype, const void* in, void* out, int rows, int ld, 
     ++g_launches;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("pack_transpose launch: ") + cudaGetErrorString(e));
+    return LP2D_OK;
+}
+
+int lp2d_transpose(int dtype, const void* in, void* out, int n, long long batch, void* stream) {
+    if (!LP2D_DTYPE_OK(dtype) || in == nullptr || out == nullptr || n <= 0 || batch < 0 || in == out)
+        return set_error(LP2D_EINVAL, "transpose: bad arguments (buffers must be distinct)");
+    if (batch == 0) return LP2D_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32), (unsigned)(batch < 1024 ? batch : 1024)), block(32, 8);
+    if (dtype == LP2D_C64) transpose_kernel<float><<<grid, block, 0, s>>>(static_cast<const float2*>(in), static_cast<float2*>(out), n, batch);
+    else transpose_kernel<double><<<grid, block, 0, s>>>(static_cast<const double2*>(in), static_cast<double2*>(out), n, batch);
+    ++g_launches;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("transpose launch: ") + cudaGetErrorString(e));
     return LP2D_OK;
 }
 

@@ -16,6 +16,13 @@ static const P2Ops<float> kP2F32[] = {
     T3Inst<float, 1024, 32, 8, 2, 3>::entry(),
     T3Inst<float, 1024, 32, 8, 2, 0>::entry(),
     T3Inst<float, 1024, 32, 4, 3>::entry(),
+#if defined(LP2D_ABLATION) && LP2D_ABLATION
+    // data-movement skeletons (HOOKS bit 2: no transform, bit 3: no factor): wrong results, timing experiments only
+    // (profiles/r3b_ablate.log: 5.1-5.3 us per beam without any arithmetic against 6.5 with it)
+    T3Inst<float, 1024, 32, 8, 2, 4>::entry(),
+    T3Inst<float, 1024, 32, 8, 2, 8>::entry(),
+    T3Inst<float, 1024, 32, 8, 2, 12>::entry(),
+#endif
     T3Inst<float, 512, 32, 8, 3>::entry(),
     T3Inst<float, 512, 32, 16, 2>::entry(),
     T3Inst<float, 256, 16, 16, 4>::entry(),
@@ -25,6 +32,14 @@ static const Q4Ops<float> kQ4F32[] = {
     Q4Inst<float, 1024, 32, 8, 2, 2>::entry(),
     Q4Inst<float, 1024, 32, 8, 2, 3>::entry(),
     Q4Inst<float, 1024, 32, 8, 2, 0>::entry(),
+    // half tiles, two CTAs per SM: their load/store and floating-point phases interleave
+    Q4Inst<float, 1024, 32, 4, 2, 2, 2>::entry(),
+    Q4Inst<float, 1024, 32, 4, 2, 3, 2>::entry(),
+#if defined(LP2D_ABLATION) && LP2D_ABLATION
+    Q4Inst<float, 1024, 32, 8, 2, 4>::entry(),
+    Q4Inst<float, 1024, 32, 8, 2, 12>::entry(),
+    Q4Inst<float, 1024, 32, 4, 2, 12, 2>::entry(),
+#endif
     Q4Inst<float, 512, 32, 16, 2>::entry(),
     Q4Inst<float, 512, 32, 16, 1>::entry(),
     Q4Inst<float, 256, 16, 16, 2>::entry(),

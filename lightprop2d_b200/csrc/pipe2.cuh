@@ -57,6 +57,8 @@ struct P2Stage {
     int inverse;         // inverse transform (ignored when mid)
     int in_ring, out_ring;
     int mask_kind;
+    int out_t;           // final column stage: out / inten are written TRANSPOSED (line c of the tile = row c of the
+                         // destination plane): contiguous 8 KB rows instead of 64-byte pieces 8 KB apart
 };
 
 template <typename T>
@@ -280,7 +282,7 @@ struct T3Cfg {
     static_assert(THREADS >= 32 && THREADS <= 1024, "block size");
 };
 
-template <typename T, int N, int E, int W, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+template <typename T, int N, int E, int W, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV, bool OUT_T = false>
 __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, int tid) {
     using K = T3Cfg<T, N, E, W>;
     constexpr int TPL = K::TPL;
@@ -288,9 +290,14 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
     constexpr long long PSTRIDE = (AXIS == AX_ROW) ? 1 : N;
     constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CTA;
     constexpr bool REV = MID || INV;
+    static_assert(!OUT_T || (AXIS == AX_COL && IN_RING && !OUT_RING && !MID), "transposed output: final column stage");
     const P2Stage<T>& st = p.st[S];
     const int l = (AXIS == AX_ROW) ? tid / TPL : tid % W;
     const int t = (AXIS == AX_ROW) ? tid % TPL : tid / W;
+    // transposed output: after the first exchange a thread works on line lo at positions to + TPL*m (a warp = a line)
+    const int lo = OUT_T ? tid / TPL : l;
+    const int to = OUT_T ? tid % TPL : t;
+    constexpr int OSTRIDE = (AXIS == AX_ROW || OUT_T) ? 1 : N;
     cx<T>* sline = xbuf + l * K::LS;
     const long long b0 = (long long)it.g * p.G;
     const long long slot0 = (long long)(it.g % p.ring_slots) * p.G;
@@ -299,9 +306,10 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
     const int fixed = it.tile * W + l;
     const long long off0 = (AXIS == AX_ROW) ? (long long)fixed * N : fixed;
     // (offsets inside a plane fit 32 bits: fewer live registers across the transform than 64-bit ones)
-    const int o_first = (REV ? ((N - t) & (N - 1)) : t) * (int)PSTRIDE;
-    const int o_base = (REV ? (N - t) : t) * (int)PSTRIDE;
-    constexpr int o_step = (REV ? -TPL : TPL) * (int)PSTRIDE;
+    const long long off0o = OUT_T ? (long long)(it.tile * W + lo) * N : off0;
+    const int o_first = (REV ? ((N - to) & (N - 1)) : to) * OSTRIDE;
+    const int o_base = (REV ? (N - to) : to) * OSTRIDE;
+    constexpr int o_step = (REV ? -TPL : TPL) * OSTRIDE;
     const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
     const cx<T>* fline = p.fac + (long long)fixed * p.fac_stride;   // L2-resident factor row of this line
 
@@ -317,7 +325,7 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
 #pragma unroll
                 for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
             }
-            if (use_pre) {
+            if (use_pre && !(HOOKS & 8)) {
                 if constexpr (AXIS == AX_ROW) {
                     p2_apply_factor_row<T, N, E, (E / 2 < 8 ? E / 2 : 8)>(v, fline, p.fac_map, t);
                 } else {
@@ -348,8 +356,8 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
             if constexpr (OUT_RING) {
                 p2_st_ring<2>(p.ring + (slot0 + bi) * PLANE + off0 + o, val);     // L2 evict-last: re-read by the next stage
             } else {
-                if (st.out != nullptr) __stcs(st.out + b * PLANE + off0 + o, val);
-                if (st.inten != nullptr) __stcs(st.inten + b * PLANE + off0 + o, val.x * val.x + val.y * val.y);
+                if (st.out != nullptr) __stcs(st.out + b * PLANE + off0o + o, val);
+                if (st.inten != nullptr) __stcs(st.inten + b * PLANE + off0o + o, val.x * val.x + val.y * val.y);
             }
         };
         // HOOKS bit 0: state stores inside the first radix pass, bit 1: result stores inside the last one; otherwise
@@ -365,6 +373,10 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
             }
             if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, NoHook(), post_hook);
             else line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+        } else if constexpr (OUT_T) {
+            cx<T>* slo = xbuf + lo * K::LS;
+            if constexpr ((HOOKS & 2) != 0) line_fft_remap<T, N, E, SYNC, false>(v, sline, t, l, slo, to, lo, p.tw, post_hook);
+            else line_fft_remap<T, N, E, SYNC, false>(v, sline, t, l, slo, to, lo, p.tw, NoHook());
         } else {
             if constexpr (!IN_RING && (HOOKS & 1) == 0) {
 #pragma unroll
@@ -373,7 +385,7 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
             if constexpr (!IN_RING && (HOOKS & 1) != 0 && (HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, pre_hook, post_hook);
             else if constexpr (!IN_RING && (HOOKS & 1) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, pre_hook, NoHook());
             else if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, false>(v, sline, p.tw, t, l, NoHook(), post_hook);
-            else line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
+            else if constexpr ((HOOKS & 4) == 0) line_fft<T, N, E, SYNC>(v, sline, p.tw, t, l);
         }
         if constexpr ((HOOKS & 2) == 0) {
 #pragma unroll
@@ -556,6 +568,8 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
             else t3_item<T, N, E, W, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
         } else if (it.s == 1) {
             if (p.st[1].mid) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
+            else if (p.st[1].out_t && p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true>(p, it, xbuf, tid);
+            else if (p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false, true>(p, it, xbuf, tid);
             else if (p.use_tma && p.st[1].inverse) t3_col_tma_item<T, N, E, W, true>(p, it, xbuf, &s_bar, tma_parity, tid);
             else if (p.use_tma) t3_col_tma_item<T, N, E, W, false>(p, it, xbuf, &s_bar, tma_parity, tid);
             else if (p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);

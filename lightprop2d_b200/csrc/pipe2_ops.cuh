@@ -86,17 +86,17 @@ struct T3Inst {
     }
 };
 
-template <typename T, int N, int E, int W, int NBUF, int HOOKS = 2>
+template <typename T, int N, int E, int W, int NBUF, int HOOKS = 2, int MINB = 1>
 struct Q4Inst {
     using K = Q4Cfg<T, N, E, W, NBUF>;
     using LP = LinePlan<N, E>;
     static cudaError_t launch(const P2Args<T>& a, unsigned grid, cudaStream_t s) {
-        q4_kernel<T, N, E, W, NBUF, HOOKS><<<grid, K::THREADS, K::SMEM, s>>>(a);
+        q4_kernel<T, N, E, W, NBUF, HOOKS, MINB><<<grid, K::THREADS, K::SMEM, s>>>(a);
         ++g_launches;
         return cudaGetLastError();
     }
     static cudaError_t configure(int* ctas) {
-        auto kern = q4_kernel<T, N, E, W, NBUF, HOOKS>;
+        auto kern = q4_kernel<T, N, E, W, NBUF, HOOKS, MINB>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, kern, K::THREADS, K::SMEM);

@@ -23,6 +23,11 @@
 
 namespace lp2d {
 
+// Phase clocks of the transform warps (tools/q4_timing.py): compiled in only with -DLP2D_Q4_CLOCKS=1 (build with
+// LP2D_BUILD_DEFS="-DLP2D_Q4_CLOCKS=1"); even a never-taken branch on p.timing costs the plain fft2 8 % (4.83 -> 5.3 us).
+#ifndef LP2D_Q4_CLOCKS
+#define LP2D_Q4_CLOCKS 0
+#endif
 enum { Q4_NDONE = 4 };       // (named barrier 15 belongs to the consumer threads, fft_core.cuh)
 
 template <typename T, int N, int E, int W, int NBUF>
@@ -44,7 +49,6 @@ struct Q4Cfg {
     static constexpr int SYNC_ROW = (TPL <= 32) ? SYNC_WARP : SYNC_NAMED;
     static constexpr int BOX = (N < 256) ? N : 256;        // rows per TMA box of a column tile
     static constexpr int FL = N / 2 + 2;
-    static_assert(NCT == LP2D_Q4_CONSUMER_THREADS, "the consumer barrier is compiled for 256 threads");
     static_assert(NCT % 32 == 0 && (W * SZ) % 16 == 0 && W <= 256, "tile shape");
     static_assert(TPL <= 32 || (TPL % 32 == 0 && W <= 14), "named row barriers");
     static_assert(SMEM <= 227 * 1024, "shared memory");
@@ -74,8 +78,9 @@ __device__ __forceinline__ void q4_mbar_wait_idle(uint64_t* bar, uint32_t parity
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+template <int NCT>
 __device__ __forceinline__ void q4_consumer_barrier() {
-    asm volatile("bar.sync 15, %0;" ::"n"(LP2D_Q4_CONSUMER_THREADS) : "memory");
+    asm volatile("bar.sync 15, %0;" ::"n"(NCT) : "memory");
 }
 // 1-D bulk copy global -> shared, completion on an mbarrier; the source is read once (evict first)
 __device__ __forceinline__ void q4_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, bool stream) {
@@ -95,8 +100,9 @@ __device__ __forceinline__ void q4_bulk_load(void* smem_dst, const void* gsrc, u
 // Row item, tile in registers: the warp hands its part of the landing buffer back.  The exchange region of a line is
 // private to its warp in row items, but the threads of a COLUMN item's line are spread over all warps: the first row
 // item after a column item waits until every warp has left that item's last gather.
+template <int NCT>
 __device__ __forceinline__ void q4_row_release(uint64_t* empty_bar, int ctid, bool after_column_item) {
-    if (after_column_item) q4_consumer_barrier();
+    if (after_column_item) q4_consumer_barrier<NCT>();
     else __syncwarp();
     if ((ctid & 31) == 0) q4_mbar_arrive(empty_bar);
 }
@@ -126,7 +132,7 @@ __device__ __forceinline__ void q4_wait_ready(const P2Args<T>& p, int item, unsi
 }
 
 // One item on the consumer threads.  `land` holds the tile: rows as [line][N] (dense), columns as [row][W].
-template <typename T, int N, int E, int W, int NBUF, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV>
+template <typename T, int N, int E, int W, int NBUF, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV, bool OUT_T = false>
 __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, const cx<T>* __restrict__ land, cx<T>* xbuf,
                                         const cx<T>* __restrict__ stw, uint64_t* empty_bar, int ctid, bool after_column_item,
                                         long long* tmark) {
@@ -134,19 +140,25 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
     constexpr int TPL = K::TPL;
     constexpr long long PLANE = (long long)N * N;
     constexpr long long PSTRIDE = (AXIS == AX_ROW) ? 1 : N;
-    constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CONSUMERS;
+    constexpr int SYNC = (AXIS == AX_ROW) ? K::SYNC_ROW : SYNC_CONSUMERS + K::NCT;
     constexpr bool REV = MID || INV;
     const P2Stage<T>& st = p.st[S];
+    static_assert(!OUT_T || (AXIS == AX_COL && IN_RING && !OUT_RING && !MID), "transposed output: final column stage");
     const int l = (AXIS == AX_ROW) ? ctid / TPL : ctid % W;
     const int t = (AXIS == AX_ROW) ? ctid % TPL : ctid / W;
+    // transposed output (see t3_item): after the first exchange a thread works on line lo at positions to + TPL*m
+    const int lo = OUT_T ? ctid / TPL : l;
+    const int to = OUT_T ? ctid % TPL : t;
+    constexpr long long OSTRIDE = (AXIS == AX_ROW || OUT_T) ? 1 : N;
     cx<T>* sline = xbuf + l * K::LS;
     const long long b = it.g;                              // one beam per group
     const long long slot = it.g % p.ring_slots;
     const int fixed = it.tile * W + l;
     const long long off0 = (AXIS == AX_ROW) ? (long long)fixed * N : fixed;
-    const long long o_first = (REV ? (long long)((N - t) & (N - 1)) : (long long)t) * PSTRIDE;
-    const long long o_base = (REV ? (long long)(N - t) : (long long)t) * PSTRIDE;
-    constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * PSTRIDE;
+    const long long off0o = OUT_T ? (long long)(it.tile * W + lo) * N : off0;
+    const long long o_first = (REV ? (long long)((N - to) & (N - 1)) : (long long)to) * OSTRIDE;
+    const long long o_base = (REV ? (long long)(N - to) : (long long)to) * OSTRIDE;
+    constexpr long long o_step = (REV ? -(long long)TPL : (long long)TPL) * OSTRIDE;
     const bool use_pre = !IN_RING && !MID && st.pre != P2_FAC_NONE;
     const cx<T>* fline = p.fac + (long long)fixed * p.fac_stride;      // L2-resident factor row of this line
     const bool keep_ring = (p.hints & P2_HINT_KEEP_RING) != 0;
@@ -154,15 +166,15 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
     cx<T> v[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = (AXIS == AX_ROW) ? land[l * N + t + TPL * m] : land[(t + TPL * m) * W + l];
-    if (AXIS == AX_ROW) q4_row_release(empty_bar, ctid, after_column_item);
-    if (tmark) tmark[1] = clock64();                       // tile in registers
+    if (AXIS == AX_ROW) q4_row_release<K::NCT>(empty_bar, ctid, after_column_item);
+    if (LP2D_Q4_CLOCKS && tmark) tmark[1] = clock64();     // tile in registers
     if constexpr (!IN_RING) {
         if (st.mask_kind != MASK_NONE) {
             const long long mb = b * st.mask_beam_stride + off0;
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = cmul(v[m], p2_mask_value<T>(st.mask, st.mask_kind, mb + (t + TPL * m) * PSTRIDE));
         }
-        if (use_pre) {
+        if (use_pre && !(HOOKS & 8)) {
             if constexpr (AXIS == AX_ROW) {
                 p2_apply_factor_row<T, N, E, E / 2>(v, fline, p.fac_map, t);
             } else {
@@ -171,7 +183,7 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
             }
         }
     }
-    if (tmark) tmark[2] = clock64();                       // pointwise factor applied
+    if (LP2D_Q4_CLOCKS && tmark) tmark[2] = clock64();     // pointwise factor applied
     // The global stores ride on the butterflies (hooks of dft_reg): the state (spectrum * H, field * lens ...) goes out
     // while the first radix pass consumes it, the result while the last radix pass produces it.
     cx<T>* const pre_dst = (!IN_RING && st.out_pre != nullptr) ? st.out_pre + b * PLANE + off0 + t * PSTRIDE : nullptr;
@@ -179,8 +191,8 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
         if (pre_dst != nullptr) __stcs(pre_dst + (TPL * m) * PSTRIDE, val);
     };
     cx<T>* const ring_dst = OUT_RING ? p.ring + slot * PLANE + off0 : nullptr;
-    cx<T>* const out_dst = (!OUT_RING && st.out != nullptr) ? st.out + b * PLANE + off0 : nullptr;
-    T* const inten_dst = (!OUT_RING && st.inten != nullptr) ? st.inten + b * PLANE + off0 : nullptr;
+    cx<T>* const out_dst = (!OUT_RING && st.out != nullptr) ? st.out + b * PLANE + off0o : nullptr;
+    T* const inten_dst = (!OUT_RING && st.inten != nullptr) ? st.inten + b * PLANE + off0o : nullptr;
     const T scale = st.scale;
     auto post_hook = [&](int m, const cx<T>& val0) {
         const cx<T> val = cscale(val0, scale);              // (a scale of 1 is exact)
@@ -224,12 +236,19 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
         if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, NoHook(), post_hook);
         else line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l);
         post_burst();
+    } else if constexpr (OUT_T) {
+        cx<T>* slo = xbuf + lo * K::LS;
+        if constexpr ((HOOKS & 2) != 0) line_fft_remap<T, N, E, SYNC, true>(v, sline, t, l, slo, to, lo, stw, post_hook);
+        else line_fft_remap<T, N, E, SYNC, true>(v, sline, t, l, slo, to, lo, stw, NoHook());
+        if ((ctid & 31) == 0) q4_mbar_arrive(empty_bar);
+        post_burst();
     } else {
         if constexpr (!IN_RING) pre_burst();
         if constexpr (!IN_RING && (HOOKS & 1) != 0 && (HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, pre_hook, post_hook);
         else if constexpr (!IN_RING && (HOOKS & 1) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, pre_hook, NoHook());
         else if constexpr ((HOOKS & 2) != 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l, NoHook(), post_hook);
-        else line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l);
+        else if constexpr ((HOOKS & 4) == 0) line_fft<T, N, E, SYNC, 0, true>(v, sline, stw, t, l);
+        else if (AXIS == AX_COL) line_sync<SYNC, TPL>(l);
         if (AXIS == AX_COL && (ctid & 31) == 0) q4_mbar_arrive(empty_bar);
         post_burst();
     }
@@ -264,8 +283,8 @@ __device__ __forceinline__ void q4_col_private_item(const P2Args<T>& p, unsigned
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> the TMA store
 }
 
-template <typename T, int N, int E, int W, int NBUF, int HOOKS>
-__global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel(const __grid_constant__ P2Args<T> p) {
+template <typename T, int N, int E, int W, int NBUF, int HOOKS, int MINB = 1>
+__global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, MINB) q4_kernel(const __grid_constant__ P2Args<T> p) {
     using K = Q4Cfg<T, N, E, W, NBUF>;
     constexpr int Q4_NBUF = NBUF;
     // (no pointer arithmetic through integers on this array: the compiler must keep seeing shared-memory addresses,
@@ -388,10 +407,10 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
     for (unsigned int k = 0;; ++k) {
         const int buf = (int)(k % Q4_NBUF);
         long long tmarks[4];
-        long long* tm = (p.timing != nullptr) ? tmarks : nullptr;
-        if (tm) tm[0] = clock64();
+        long long* tm = (LP2D_Q4_CLOCKS && p.timing != nullptr) ? tmarks : nullptr;
+        if (LP2D_Q4_CLOCKS && tm) tm[0] = clock64();
         p2_mbar_wait(&s_full[buf], (k / Q4_NBUF) & 1u);
-        if (tm) { tm[3] = clock64(); tm[1] = tm[2] = tm[3]; }
+        if (LP2D_Q4_CLOCKS && tm) { tm[3] = clock64(); tm[1] = tm[2] = tm[3]; }
         const int item = s_desc[buf];
         if (item >= 0) {
             P2Item it;
@@ -411,6 +430,8 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
                     }
                 }
                 if (p.st[1].mid) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, true, true, false>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
+                else if (p.st[1].out_t && p.st[1].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, true, true>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
+                else if (p.st[1].out_t) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
                 else if (p.st[1].inverse) q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, true>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
                 else q4_item<T, N, E, W, NBUF, HOOKS, 1, AX_COL, true, false, false, false>(p, it, land, xbuf, stw, eb, tid, after_col, tm);
             } else {
@@ -421,7 +442,7 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, 1) q4_kernel
             after_col = (it.s == 1) && p.use_tma != 2;
         }
         __syncwarp();                                      // the warp's stores of the item are issued
-        if (tm && item >= 0 && (tid & 31) == 0) {
+        if (LP2D_Q4_CLOCKS && tm && item >= 0 && (tid & 31) == 0) {
             // bins: [kind][0] wait for the tile, [1] tile -> registers, [2] factor, [3] transform + stores, [4] items
             P2Item it2;
             p2_decode<T, K::TILES>(p, item, it2);

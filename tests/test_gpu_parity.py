@@ -939,3 +939,79 @@ def test_config5_full_size(bits):
     b.construct_by_modes(dmodes, coeffs)
     want = coeffs[::9].astype(np.complex128) @ modes.astype(np.complex128)          # every 9th beam on the host
     assert rel_l2(b.field[::9].reshape(-1, n * n).cpu().numpy(), want) <= TOL[bits]
+
+
+# ------------------------------------------------- transposed spectrum layout (lp2d_plan_set_spectrum_layout)
+@pytest.mark.parametrize("bits,n", [(64, 256), (64, 512), (64, 1024), (64, 2048), (128, 256), (128, 512)])
+def test_transposed_spectrum_layout_vs_oracle(bits, n, monkeypatch):
+    """LP2D_SPECTRUM_T=1: the state is held transposed on the device, every observable keeps the reference's
+    orientation: lens / propagate / filters / init_spectrum / _update_obj against the oracle, batch of 3."""
+    from lightprop2d_b200 import beam2d as _b
+    monkeypatch.setenv("LP2D_SPECTRUM_T", "1")
+    _b._PLAN_CACHE.clear()
+    try:
+        rng = np.random.default_rng(77 + n)
+        f0 = (rng.uniform(size=(3, n, n)) * np.exp(2j * np.pi * rng.uniform(size=(3, n, n)))).astype(CT[bits])
+        area, wl = 4e-1 * n / 1024, 532e-7
+        b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+        o = orc.OracleBeam(area, n, wl, init_field=f0.copy(), complex_bits=bits)
+        assert b._st, "the plan did not take the transposed layout"
+        assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+        b.propagate(0.02); o.propagate(0.02)                       # first step: fft2 + stateful step
+        assert rel_l2(b.field, o.field) <= TOL[bits] and rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+        for f, z in ((0.1, 0.02), (-0.3, 10.0)):
+            b.lens(f); o.lens(f)
+            b.propagate(z); o.propagate(z)
+            assert rel_l2(b.field, o.field) <= TOL[bits], (f, z)
+            assert rel_l2(b.spectrum, o.spectrum) <= TOL[bits], (f, z)
+            assert rel_l2(b.iprofile, o.iprofile) <= TOL[bits], (f, z)
+        # an asymmetric spectral mask (generator + array) and a coordinate mask
+        kmask = (rng.uniform(size=(n, n)) + 1j * rng.uniform(size=(n, n))).astype(CT[bits])
+        sgen = lambda Kx, Ky, s: np.exp(-(Kx ** 2 + 2 * (Ky - 0.1 * s) ** 2) / s ** 2)  # noqa: E731
+        b.spectral_filter(f_init=kmask, f_gen=sgen, fargs=(40.,)); o.spectral_filter(f_init=kmask, f_gen=sgen, fargs=(40.,))
+        assert rel_l2(b.field, o.field) <= TOL[bits] and rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+        b.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,)); o.coordinate_filter(f_gen=lp.round_hole, fargs=(area / 3,))
+        b.propagate(-0.5); o.propagate(-0.5)
+        assert rel_l2(b.field, o.field) <= TOL[bits] and rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+        # a spectrum handed in (reference orientation) is taken over as the state
+        s_in = np.asarray(o.spectrum).copy()
+        b._update_obj(np.asarray(o.field).copy(), s_in); o.update(np.asarray(o.field).copy(), s_in.copy())
+        b.propagate(0.3); o.propagate(0.3)
+        assert rel_l2(b.field, o.field) <= TOL[bits]
+        I, _ = b.propagate_sweep(0.01, 3)
+        for _ in range(3):
+            o.propagate(0.01)
+        assert rel_l2(b.field, o.field) <= TOL[bits]
+        assert rel_l2(I[-1], np.asarray(o.iprofile)[..., n // 2, n // 2]) <= 10 * TOL[bits]
+    finally:
+        _b._PLAN_CACHE.clear()
+
+
+def test_transposed_spectrum_layout_cabi():
+    """Raw C ABI: with the transposed layout lp2d_fft2's output is bit for bit the transpose of the natural one,
+    lp2d_transpose converts, and sizes without a fused step kernel refuse the layout."""
+    lib = _lib.load()
+    n, batch = 512, 4
+    from lightprop2d_b200 import beam2d as _b
+    _b._PLAN_CACHE.clear()
+    f = torch.randn(batch, n, n, dtype=torch.complex64, device="cuda")
+    b = Beam2D(0.2, n, 532e-7, init_field=f[:1], complex_bits=64, use_gpu=True)
+    plan = b._plan.handle
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    s0, s1, t = torch.empty_like(f), torch.empty_like(f), torch.empty_like(f)
+    _lib.check(lib.lp2d_fft2(plan, f.data_ptr(), s0.data_ptr(), batch, 0, st), "fft2")
+    assert lib.lp2d_plan_get_spectrum_layout(plan) == 0
+    _lib.check(lib.lp2d_plan_set_spectrum_layout(plan, 1), "set layout")
+    assert lib.lp2d_plan_get_spectrum_layout(plan) == 1
+    _lib.check(lib.lp2d_fft2(plan, f.data_ptr(), s1.data_ptr(), batch, 0, st), "fft2")
+    _lib.check(lib.lp2d_transpose(_lib.C64, s1.data_ptr(), t.data_ptr(), n, batch, st), "transpose")
+    assert torch.equal(t, s0) and torch.equal(s1.transpose(-1, -2), s0)
+    back = torch.empty_like(f)
+    _lib.check(lib.lp2d_fft2(plan, s1.data_ptr(), back.data_ptr(), batch, 1, st), "ifft2")
+    assert rel_l2(back.cpu().numpy(), f.cpu().numpy()) <= 1e-6
+    _lib.check(lib.lp2d_plan_set_spectrum_layout(plan, 0), "set layout")
+    _b._PLAN_CACHE.clear()
+    b2 = Beam2D(0.2, 128, 532e-7, init_field=f[:1, :128, :128].contiguous(), complex_bits=64, use_gpu=True)
+    assert lib.lp2d_plan_set_spectrum_layout(b2._plan.handle, 1) == 2      # LP2D_EUNSUPPORTED
+    assert lib.lp2d_transpose(_lib.C64, s1.data_ptr(), s1.data_ptr(), n, batch, st) == 1      # LP2D_EINVAL
+    _b._PLAN_CACHE.clear()
