@@ -170,6 +170,34 @@ LP2D_API int lp2d_intensity(lp2d_plan* plan, const void* field, void* out, long 
 LP2D_API int lp2d_expand(int dtype, const void* in, void* out, int n_in, int n_out, long long batch,
                 void* stream);
 
+/* The generators of lightprop2d/profiles.py:35-136 evaluated on the device: `batch`
+ * planes of n x n samples from the coordinate tables dev_x / dev_y (device, n doubles each: Beam2D.X and Beam2D.Y --
+ * where the reference shifts them in place, profiles.py:69-70, the caller does so before the upload).
+ * out_kind: LP2D_C64 / LP2D_C128 (complex field) or LP2D_GEN_OUT_MASK (one byte per sample; 0/1 profiles only).
+ * host_params6 per kind:
+ *   PLANE_WAVE -;  RANDOM_WAVE, RANDOM_WAVE_BIN -;  GAUSSIAN_BEAM {A0, rho0};
+ *   ROUND_HOLE, RANDOM_ROUND_HOLE(_BIN, _PHASE) {R, x0, y0, -, -, 1/exp(0.5) as the host evaluates it};
+ *   RECTANGLE_HOLE {dx, dy, x0, y0} (square_hole: dx = dy);  SQUARE_SLITS {d, slits_distance, x0, y0}.
+ * Deterministic profiles use the reference's FP64 expressions in its operation order (device exp() may differ from
+ * the host's in the last bit: a sample whose Gaussian value is within one ulp of the round_hole threshold can fall
+ * on the other side).  Random profiles draw one uniform number per cell of binning_order x binning_order samples
+ * from Philox4x32-10 keyed by (seed, first_beam + b, cell): the numbers lp2d_random_fields draws, independent of
+ * batch and rank; numpy's stream is not reproduced (seeded parity uses the host generators). */
+#define LP2D_GEN_PLANE_WAVE 0
+#define LP2D_GEN_RANDOM_WAVE 1
+#define LP2D_GEN_RANDOM_WAVE_BIN 2
+#define LP2D_GEN_GAUSSIAN_BEAM 3
+#define LP2D_GEN_ROUND_HOLE 4
+#define LP2D_GEN_RANDOM_ROUND_HOLE 5
+#define LP2D_GEN_RANDOM_ROUND_HOLE_BIN 6
+#define LP2D_GEN_RANDOM_ROUND_HOLE_PHASE 7
+#define LP2D_GEN_RECTANGLE_HOLE 8
+#define LP2D_GEN_SQUARE_SLITS 9
+#define LP2D_GEN_OUT_MASK 16
+LP2D_API int lp2d_generate(int out_kind, void* out, int n, long long batch, const double* dev_x, const double* dev_y,
+                           int kind, const double* host_params6, int binning_order, unsigned long long seed,
+                           unsigned long long first_beam, void* stream);
+
 /* Beam2D.coarse (beam2d.py:456-459): mean over m x m blocks, n_in x n_in -> n_in/m x n_in/m. */
 LP2D_API int lp2d_coarse(int dtype, const void* in, void* out, int n_in, int m, long long batch,
                 void* stream);

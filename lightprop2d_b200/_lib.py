@@ -61,6 +61,7 @@ SIGNATURES = {
     "lp2d_plan_set_spectrum_layout": (_i, [_vp, _i]),
     "lp2d_plan_get_spectrum_layout": (_i, [_vp]),
     "lp2d_transpose": (_i, [_i, _vp, _vp, _i, _ll, _vp]),
+    "lp2d_generate": (_i, [_i, _vp, _i, _ll, _vp, _vp, _i, C.POINTER(C.c_double), _i, C.c_ulonglong, C.c_ulonglong, _vp]),
     "lp2d_launch_count": (_ll, []),
 }
 

@@ -35,10 +35,14 @@ static const Q4Ops<float> kQ4F32[] = {
     // half tiles, two CTAs per SM: their load/store and floating-point phases interleave
     Q4Inst<float, 1024, 32, 4, 2, 2, 2>::entry(),
     Q4Inst<float, 1024, 32, 4, 2, 3, 2>::entry(),
+    Q4Inst<float, 1024, 32, 4, 1, 2, 3>::entry(),
 #if defined(LP2D_ABLATION) && LP2D_ABLATION
     Q4Inst<float, 1024, 32, 8, 2, 4>::entry(),
     Q4Inst<float, 1024, 32, 8, 2, 12>::entry(),
     Q4Inst<float, 1024, 32, 4, 2, 12, 2>::entry(),
+    Q4Inst<float, 1024, 32, 8, 2, 2 + 16>::entry(),        // transform, no result stores
+    Q4Inst<float, 1024, 32, 8, 2, 2 + 32>::entry(),        // transform, no state stores
+    Q4Inst<float, 1024, 32, 8, 2, 2 + 48>::entry(),        // transform, no stores at all
 #endif
     Q4Inst<float, 512, 32, 16, 2>::entry(),
     Q4Inst<float, 512, 32, 16, 1>::entry(),

@@ -88,7 +88,7 @@ struct T3Inst {
 
 template <typename T, int N, int E, int W, int NBUF, int HOOKS = 2, int MINB = 1>
 struct Q4Inst {
-    using K = Q4Cfg<T, N, E, W, NBUF>;
+    using K = Q4Cfg<T, N, E, W, NBUF, (MINB >= 3 ? 1 : 2)>;
     using LP = LinePlan<N, E>;
     static cudaError_t launch(const P2Args<T>& a, unsigned grid, cudaStream_t s) {
         q4_kernel<T, N, E, W, NBUF, HOOKS, MINB><<<grid, K::THREADS, K::SMEM, s>>>(a);

@@ -30,13 +30,16 @@ namespace lp2d {
 #endif
 enum { Q4_NDONE = 4 };       // (named barrier 15 belongs to the consumer threads, fft_core.cuh)
 
-template <typename T, int N, int E, int W, int NBUF>
+// HW: helper warps: 2 = producer warp + signaller warp; 1 = both in one warp (lanes 0 and 16), which leaves the
+// registers of a warp to the transform warps when three CTAs share an SM
+template <typename T, int N, int E, int W, int NBUF, int HW = 2>
 struct Q4Cfg {
     using P = LinePlan<N, E>;
     static constexpr int TPL = P::TPL;
     static constexpr int NCT = TPL * W;                    // consumer threads
     static constexpr int NCW = NCT / 32;                   // consumer warps
-    static constexpr int THREADS = NCT + 64;               // + producer warp + signaller warp
+    static constexpr int THREADS = NCT + 32 * HW;          // + producer warp + signaller warp
+    static constexpr int SIGNALLER = (HW == 2) ? 32 : 16;  // helper-thread index of the signaller
     static constexpr int TILES = N / W;
     static constexpr int SZ = (int)sizeof(cx<T>);
     static constexpr int S128 = 128 / SZ;
@@ -188,6 +191,7 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
     // while the first radix pass consumes it, the result while the last radix pass produces it.
     cx<T>* const pre_dst = (!IN_RING && st.out_pre != nullptr) ? st.out_pre + b * PLANE + off0 + t * PSTRIDE : nullptr;
     auto pre_hook = [&](int m, const cx<T>& val) {
+        if ((HOOKS & 32) && !(p.hints & (1 << 20))) return;  // ablation: no state stores
         if (pre_dst != nullptr) __stcs(pre_dst + (TPL * m) * PSTRIDE, val);
     };
     cx<T>* const ring_dst = OUT_RING ? p.ring + slot * PLANE + off0 : nullptr;
@@ -195,6 +199,7 @@ __device__ __forceinline__ void q4_item(const P2Args<T>& p, const P2Item it, con
     T* const inten_dst = (!OUT_RING && st.inten != nullptr) ? st.inten + b * PLANE + off0o : nullptr;
     const T scale = st.scale;
     auto post_hook = [&](int m, const cx<T>& val0) {
+        if ((HOOKS & 16) && !(p.hints & (1 << 20))) return;  // ablation: transform but no result stores (timing only)
         const cx<T> val = cscale(val0, scale);              // (a scale of 1 is exact)
         const long long o = (m == 0) ? o_first : o_base + m * o_step;
         if constexpr (OUT_RING) {
@@ -284,8 +289,8 @@ __device__ __forceinline__ void q4_col_private_item(const P2Args<T>& p, unsigned
 }
 
 template <typename T, int N, int E, int W, int NBUF, int HOOKS, int MINB = 1>
-__global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, MINB) q4_kernel(const __grid_constant__ P2Args<T> p) {
-    using K = Q4Cfg<T, N, E, W, NBUF>;
+__global__ void __launch_bounds__((Q4Cfg<T, N, E, W, NBUF, (MINB >= 3 ? 1 : 2)>::THREADS), MINB) q4_kernel(const __grid_constant__ P2Args<T> p) {
+    using K = Q4Cfg<T, N, E, W, NBUF, (MINB >= 3 ? 1 : 2)>;
     constexpr int Q4_NBUF = NBUF;
     // (no pointer arithmetic through integers on this array: the compiler must keep seeing shared-memory addresses,
     // or every tile access becomes a generic LD / ST that queues with the global accesses)
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(Q4Cfg<T, N, E, W, NBUF>::THREADS, MINB) q4_ker
                                        (int)((it.g % p.ring_slots) * N) + q * K::BOX, &s_full[buf]);
                 }
             }
-        } else if (h == 32) {
+        } else if (h == K::SIGNALLER) {
             // ----------------------------------------------------------------- signaller
             for (unsigned int k = 0;; ++k) {
                 q4_mbar_wait_idle(&s_done[k % Q4_NDONE], (k / Q4_NDONE) & 1u);

@@ -99,28 +99,17 @@ class EnsemblePropagator:
     def random_fields(self, batch, R, x0=0., y0=0., seed=0, first_beam=0, phase=False, out=None):
         """``batch`` input fields generated on the device: ``profiles.random_round_hole`` (``phase=False``:
         amplitude uniform in [0, 1) inside the aperture) or ``profiles.random_round_hole_phase``
-        (``phase=True``: exp(2 pi i u) inside), zero outside (profiles.py:94-113).  The aperture is the
-        host-built ``round_hole(X, Y, R, x0, y0)`` array -- exactly the reference's -- uploaded once; the
+        (``phase=True``: exp(2 pi i u) inside), zero outside (profiles.py:94-113).  Aperture and numbers are evaluated on the device
+        (``device_profiles``, ``lp2d_generate``: the reference's FP64 ``round_hole`` expression per sample); the
         uniform numbers come from a counter-based generator keyed by (seed, first_beam + b, sample), so
         beam ``first_beam + b`` is the same whatever batch or rank generates it (shard with
         ``shard_range`` and pass the block start as ``first_beam``)."""
-        torch = _torch()
-        from . import profiles
-        key = (float(R), float(x0), float(y0))
-        if getattr(self, "_mask_key", None) != key:
-            dL = self.area_size / self.npoints
-            X = np.arange(-self.npoints // 2, self.npoints // 2, 1) * dL
-            m = profiles.round_hole(X.copy(), X.reshape((-1, 1)).copy(), R, x0, y0)
-            self._mask_dev = torch.from_numpy(np.ascontiguousarray(m.astype(np.uint8))).to(self._tdev)
-            self._mask_key = key
-        n = self.npoints
-        if out is None:
-            out = torch.empty((int(batch), n, n), dtype=self._cdtype, device=self._tdev)
-        with torch.cuda.device(self._tdev):
-            _lib.check(self._lib.lp2d_random_fields(_lib.C64 if self.complex_bits == 64 else _lib.C128, out.data_ptr(),
-                                                    self._mask_dev.data_ptr(), n, int(batch), int(first_beam), int(seed),
-                                                    1 if phase else 0, self._stream()), "random_fields")
-        return out
+        from . import device_profiles as dp
+        dL = self.area_size / self.npoints
+        X = np.arange(-self.npoints // 2, self.npoints // 2, 1) * dL
+        gen = dp.random_round_hole_phase if phase else dp.random_round_hole
+        return gen(X, X.reshape((-1, 1)), R, x0, y0, batch=int(batch), complex_bits=self.complex_bits, device=self.device,
+                   seed=int(seed), first_beam=int(first_beam), out=out)
 
     def intensity(self, fields, z, out=None, work=None):
         """|ifft2(fft2(fields) * H(z))|^2 for device ``fields`` of shape (B, N, N); returns a device tensor.

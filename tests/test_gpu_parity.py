@@ -1015,3 +1015,86 @@ def test_transposed_spectrum_layout_cabi():
     assert lib.lp2d_plan_set_spectrum_layout(b2._plan.handle, 1) == 2      # LP2D_EUNSUPPORTED
     assert lib.lp2d_transpose(_lib.C64, s1.data_ptr(), s1.data_ptr(), n, batch, st) == 1      # LP2D_EINVAL
     _b._PLAN_CACHE.clear()
+
+
+# ----------------------------------------------------------- generators on the device (lp2d_generate)
+@pytest.mark.parametrize("n", [256, 250])
+def test_device_profiles_match_host_generators(n):
+    """device_profiles.* against profiles.* (profiles.py:35-136): deterministic profiles sample for sample, random ones
+    by their structure (range, aperture, cells of binning_order^2 equal samples, shard invariance, mean)."""
+    from lightprop2d_b200 import device_profiles as dp
+    area = 400 * um
+    X = np.arange(-n // 2, n // 2) * (area / n)
+    g = lambda: (X.copy(), X.reshape(-1, 1).copy())  # noqa: E731
+    cases = [("plane_wave", ()), ("round_hole", (150 * um,)), ("round_hole", (90 * um, 30 * um, -20 * um)),
+             ("rectangle_hole", (200 * um, 100 * um)), ("rectangle_hole", (120 * um, 60 * um, 25 * um, -40 * um)),
+             ("square_hole", (150 * um,)), ("square_hole", (80 * um, -30 * um, 45 * um)),
+             ("square_slits", (40 * um, 120 * um)), ("square_slits", (30 * um, 100 * um, 15 * um, -10 * um))]
+    for name, args in cases:
+        host = getattr(lp, name)(*g(), *args)
+        dev = getattr(dp, name)(*g(), *args)
+        if name == "plane_wave":
+            assert dev.dtype == torch.complex128 and np.array_equal(dev.cpu().numpy().real, host)
+            continue
+        assert dev.dtype == torch.bool and dev.shape == (n, n)
+        assert np.array_equal(dev.cpu().numpy(), host), (name, args, int((dev.cpu().numpy() != host).sum()))
+        asfield = getattr(dp, name)(*g(), *args, mask=False, complex_bits=64)
+        assert asfield.dtype == torch.complex64 and np.array_equal(asfield.cpu().numpy().real != 0, host)
+    # gaussian_beam: FP64 expression, the in-place shift of its arguments included
+    xh, yh = g(); xd, yd = g()
+    host = lp.gaussian_beam(xh, yh, 1.3, 70 * um, 11 * um, -7 * um)
+    dev = dp.gaussian_beam(xd, yd, 1.3, 70 * um, 11 * um, -7 * um)
+    assert np.array_equal(xh, xd) and np.array_equal(yh, yd) and not np.array_equal(xd, X)
+    assert rel_l2(dev.cpu().numpy(), host.astype(np.complex128)) <= 1e-15
+    # random profiles
+    hole = lp.round_hole(*g(), 150 * um)
+    bo = 2 if n % 2 == 0 else 1
+    for name, args, binary in (("random_wave", (), False), ("random_wave_bin", (), True), ("random_round_hole", (150 * um,), False),
+                               ("random_round_hole_bin", (150 * um,), True), ("random_round_hole_phase", (150 * um,), False)):
+        f = getattr(dp, name)(*g(), *args, batch=6, complex_bits=64, seed=42).cpu().numpy()
+        assert f.shape == (6, n, n)
+        if "round_hole" in name:
+            assert np.all(f[:, ~hole] == 0)
+            inside = f[:, hole]
+        else:
+            inside = f.reshape(6, -1)
+        if name.endswith("phase"):
+            assert np.allclose(np.abs(inside), 1, atol=1e-6) and abs(inside.mean()) < 2e-2
+        else:
+            assert np.all(f.imag == 0) and inside.real.min() >= 0 and inside.real.max() < 1 + binary
+            assert abs(inside.real.mean() - 0.5) < 1e-2
+            if binary:
+                assert set(np.unique(inside.real)) <= {0.0, 1.0}
+        part = getattr(dp, name)(*g(), *args, batch=2, complex_bits=64, seed=42, first_beam=3).cpu().numpy()
+        assert np.array_equal(part, f[3:5])                      # a beam does not depend on the batch it is generated in
+        if bo > 1:
+            kw = dict(binning_order=bo)
+            fb = getattr(dp, name)(*g(), *args, batch=2, complex_bits=64, seed=5, **kw).cpu().numpy()
+            cells = fb if "round_hole" not in name else None
+            if cells is not None:                                # every bo x bo cell holds one value
+                c = cells.reshape(2, n // bo, bo, n // bo, bo)
+                assert np.all(c == c[:, :, :1, :, :1])
+    f128 = dp.random_round_hole(*g(), 150 * um, batch=2, complex_bits=128, seed=1).cpu().numpy()
+    assert f128.dtype == np.complex128 and len(np.unique(f128.real[:, hole])) > 0.99 * 2 * hole.sum()
+
+
+def test_device_profiles_drive_beam2d():
+    """A device generator as ``init_field_gen`` / ``f_gen`` of Beam2D: same results as the host generator."""
+    from functools import partial
+    from lightprop2d_b200 import device_profiles as dp
+    n, area, wl = 512, 3 * mm, 632 * nm
+    args = (1., 0.03, 0.011, -0.007)
+    for bits in BITS:
+        b = Beam2D(area, n, wl, init_field_gen=partial(dp.gaussian_beam, complex_bits=bits), init_gen_args=args, complex_bits=bits)
+        o = orc.OracleBeam(area, n, wl, init_field_gen=lp.gaussian_beam, init_gen_args=args, complex_bits=bits)
+        assert np.array_equal(b.X, o.X)                          # the in-place shift reached Beam2D.X
+        b.coordinate_filter(f_gen=dp.round_hole, fargs=(0.08,)); o.coordinate_filter(f_gen=lp.round_hole, fargs=(0.08,))
+        b.lens(2.); o.lens(2.)
+        b.propagate(0.7); o.propagate(0.7)
+        assert rel_l2(b.field, o.field) <= TOL[bits] and rel_l2(b.iprofile, o.iprofile) <= TOL[bits]
+    ens = Beam2D(200 * um, 256, wl, init_field_gen=partial(dp.random_round_hole_phase, batch=8, complex_bits=64, seed=3),
+                 init_gen_args=(25 * um,), complex_bits=64, use_gpu=True, numpy_output=False)
+    assert tuple(ens.field.shape) == (8, 256, 256)
+    e0 = float((ens.iprofile).sum())
+    ens.propagate(100 * um)
+    assert abs(float(ens.iprofile.sum()) - e0) <= 1e-4 * e0
