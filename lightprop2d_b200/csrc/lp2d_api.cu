@@ -503,6 +503,7 @@ int run_q4(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
            long long batch, cudaStream_t s) {
     const Q4Ops<T>* ops = q4_of<T>(p);
     if (ops == nullptr) return -1;
+    if (stages[nstages - 1].moments != nullptr) return -1;      // the fused moment sums live in the ticket form
     // bulk copies of the user rows need 16-byte aligned planes
     if (!stages[0].in_ring && (reinterpret_cast<uintptr_t>(stages[0].in) & 15) != 0) return -1;
     const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
@@ -641,6 +642,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
             if (st.out_pre) st.out_pre += off;
             if (st.out_mid) st.out_mid += off;
             if (st.inten) st.inten += off;
+            if (st.moments) st.moments += b0 * 5;
             if (st.mask) st.mask = static_cast<const char*>(st.mask) + b0 * st.mask_beam_stride *
                                    (st.mask_kind == MASK_CX ? sizeof(cx<T>) : st.mask_kind == MASK_REAL ? sizeof(T) : 1);
         }
@@ -658,7 +660,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.fac_stride = (fac_kind == P2_FAC_LENS && !p->x2_even) ? p->n : ops->fl;
         a.hints = p->pipe_hints >= 0 ? p->pipe_hints : (P2_HINT_KEEP_RING | 1 | (nstages == 2 ? P2_HINT_PREFETCH : 0));
         a.use_tma = 0;
-        if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && !a.st[1].out_t && a.st[1].out != nullptr &&
+        if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && !a.st[1].out_t && a.st[1].moments == nullptr && a.st[1].out != nullptr &&
             (ops->w * (int)sizeof(cx<T>)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.st[1].out) & 15) == 0) {
             const int box_rows = p->n < 256 ? p->n : 256;
             if (encode_plane_map(&a.tm_ring, p->ring, p->n, (long long)slots * G, (int)sizeof(cx<T>), ops->w, box_rows) &&
@@ -816,7 +818,7 @@ int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const v
 
 template <typename T>
 int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
-                    cudaStream_t s) {
+                    cudaStream_t s, double* moments = nullptr, double dL = 0.0, bool* moments_done = nullptr) {
     const T sc = (T)(1.0 / (double)p->n);
     {
         // rows: spectrum *= H (state stored back), inverse row transform -> ring; columns: inverse -> field
@@ -831,8 +833,12 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         // transposed spectrum: a memory row is a grid COLUMN of the spectrum (factor rows by column), and the column
         // stage's transposed store lands the field in its natural orientation
         st[1].out_t = p->spectrum_t;
+        st[1].moments = moments; st[1].dL = dL;                 // (zeroed by the caller; the per-pass path below ignores them)
         const int rc = (p->spectrum_t || (p->fused_ops & 2)) ? run_p2<T>(p, st, 2, P2_FAC_H, p->spectrum_t, z, 0.0, batch, s, 2) : -1;
-        if (rc >= 0) return rc;
+        if (rc >= 0) {
+            if (moments_done != nullptr) *moments_done = (rc == 0 && moments != nullptr);
+            return rc;
+        }
         if (p->spectrum_t) return fail(LP2D_EUNSUPPORTED, "transposed spectrum layout: the fused step kernel does not apply to this call");
     }
     const long long plane = (long long)p->n * p->n;
@@ -966,9 +972,13 @@ int lp2d_propagate_sweep(lp2d_plan* p, void* spectrum, void* field, long long ba
     if (batch == 0 || nsteps == 0 || dz == 0) return LP2D_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t rsz = p->dtype == LP2D_C64 ? sizeof(float) : sizeof(double);
+    if (moments_out != nullptr)                                 // the fused step accumulates into it (atomics)
+        LP2D_CU(cudaMemsetAsync(moments_out, 0, (size_t)nsteps * batch * 5 * sizeof(double), s), "propagate_sweep: memset");
     for (int k = 0; k < nsteps; ++k) {
-        const int rc = p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, nullptr, batch, dz, s)
-                                            : propagate_state<double>(p, spectrum, field, nullptr, batch, dz, s);
+        bool fused_moments = false;
+        double* mk_ = moments_out ? moments_out + (size_t)k * batch * 5 : nullptr;
+        const int rc = p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, nullptr, batch, dz, s, mk_, dL, &fused_moments)
+                                            : propagate_state<double>(p, spectrum, field, nullptr, batch, dz, s, mk_, dL, &fused_moments);
         if (rc) return rc;
         if (probe_out != nullptr) {
             char* dst = static_cast<char*>(probe_out) + (size_t)k * batch * rsz;
@@ -981,7 +991,7 @@ int lp2d_propagate_sweep(lp2d_plan* p, void* spectrum, void* field, long long ba
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return cuda_fail(e, "probe launch");
         }
-        if (moments_out != nullptr) {
+        if (moments_out != nullptr && !fused_moments) {
             const size_t csz = p->dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2);
             for (long long b = 0; b < batch; ++b) {
                 const int rc2 = lp2d_moments(p->dtype, static_cast<const char*>(field) + (size_t)b * plane * csz, p->n, dL, 0.0, 0.0,

@@ -57,6 +57,8 @@ struct P2Stage {
     int inverse;         // inverse transform (ignored when mid)
     int in_ring, out_ring;
     int mask_kind;
+    double* moments;     // final column stage, or nullptr: [beam][5] += sum I, sum x I, sum y I, sum x^2 I, sum y^2 I of the
+    double dL;           // stage's output (x = (col - N/2) dL, y = (row - N/2) dL; beam2d.py:680-684, 696-702); zeroed by the host
     int out_t;           // final column stage: out / inten are written TRANSPOSED (line c of the tile = row c of the
                          // destination plane): contiguous 8 KB rows instead of 64-byte pieces 8 KB apart
 };
@@ -283,7 +285,7 @@ struct T3Cfg {
 };
 
 template <typename T, int N, int E, int W, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV, bool OUT_T = false>
-__device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, int tid) {
+__device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, int tid, double (*s_mom)[5] = nullptr) {
     using K = T3Cfg<T, N, E, W>;
     constexpr int TPL = K::TPL;
     constexpr long long PLANE = (long long)N * N;
@@ -390,6 +392,40 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
         if constexpr ((HOOKS & 2) == 0) {
 #pragma unroll
             for (int m = 0; m < E; ++m) post_hook(m, v[m]);
+        }
+        // Moment sums of the intensity, fused into the final stage: a z-sweep reads
+        // centroid / D4sigma of every step without another pass over the field.  v[] holds the (unscaled) results.
+        if constexpr (AXIS == AX_COL && !OUT_RING && !MID) {
+            if (st.moments != nullptr && s_mom != nullptr) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;                        // sums over the thread's positions along the line
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const cx<T> val = cscale(v[m], st.scale);
+                    const double I = (double)(T)(val.x * val.x + val.y * val.y);
+                    const int pos = REV ? ((N - to - TPL * m) & (N - 1)) : to + TPL * m;
+                    const double u = (double)(pos - N / 2) * st.dL;
+                    s0 += I; s1 += u * I; s2 += u * u * I;
+                }
+                const double w = (double)(it.tile * W + lo - N / 2) * st.dL;   // coordinate of the line itself
+                // natural store: the line is a grid column (x = w), positions are rows (y); transposed: the other way
+                double a[5] = {s0, OUT_T ? s1 : w * s0, OUT_T ? w * s0 : s1, OUT_T ? s2 : w * w * s0, OUT_T ? w * w * s0 : s2};
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+                }
+                __syncthreads();                                             // (scratch of the previous beam is consumed)
+                if ((tid & 31) == 0) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) s_mom[tid >> 5][k] = a[k];
+                }
+                __syncthreads();
+                if (tid < 5) {
+                    double acc = 0.0;
+                    for (int q = 0; q < K::THREADS / 32; ++q) acc += s_mom[q][tid];
+                    atomicAdd(st.moments + b * 5 + tid, acc);
+                }
+            }
         }
     }
 }
@@ -507,6 +543,7 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_item;
     __shared__ uint64_t s_bar;                             // TMA loads of the column stage
+    __shared__ double s_mom[K::THREADS / 32][5];           // CTA-level reduction of the fused moment sums
     cx<T>* xbuf = reinterpret_cast<cx<T>*>(smem_raw);
     const int tid = threadIdx.x;
     uint32_t tma_parity = 0;
@@ -568,12 +605,12 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
             else t3_item<T, N, E, W, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
         } else if (it.s == 1) {
             if (p.st[1].mid) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
-            else if (p.st[1].out_t && p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true>(p, it, xbuf, tid);
-            else if (p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false, true>(p, it, xbuf, tid);
+            else if (p.st[1].out_t && p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true>(p, it, xbuf, tid, s_mom);
+            else if (p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false, true>(p, it, xbuf, tid, s_mom);
             else if (p.use_tma && p.st[1].inverse) t3_col_tma_item<T, N, E, W, true>(p, it, xbuf, &s_bar, tma_parity, tid);
             else if (p.use_tma) t3_col_tma_item<T, N, E, W, false>(p, it, xbuf, &s_bar, tma_parity, tid);
-            else if (p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid);
-            else t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid);
+            else if (p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true>(p, it, xbuf, tid, s_mom);
+            else t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false>(p, it, xbuf, tid, s_mom);
         } else {
             t3_item<T, N, E, W, HOOKS, 2, AX_ROW, true, false, false, true>(p, it, xbuf, tid);
         }

@@ -1098,3 +1098,41 @@ def test_device_profiles_drive_beam2d():
     e0 = float((ens.iprofile).sum())
     ens.propagate(100 * um)
     assert abs(float(ens.iprofile.sum()) - e0) <= 1e-4 * e0
+
+
+@pytest.mark.parametrize("bits,n,layout_t", [(64, 512, 0), (64, 1024, 0), (64, 1024, 1), (128, 256, 0), (128, 512, 1), (64, 128, 0)])
+def test_fused_moment_sums_in_sweep(bits, n, layout_t, monkeypatch):
+    """lp2d_propagate_sweep's moment sums come out of the final stage of the fused step (no extra pass over the field):
+    against lp2d_moments on the field of every step, batch of 3, both spectrum layouts; 128 points = per-pass path."""
+    from lightprop2d_b200 import beam2d as _b
+    monkeypatch.setenv("LP2D_SPECTRUM_T", str(layout_t))
+    _b._PLAN_CACHE.clear()
+    try:
+        rng = np.random.default_rng(5 + n)
+        X = np.arange(-n // 2, n // 2) / n
+        env = np.exp(-((X[None, :] - 0.11) ** 2 + (X[:, None] + 0.07) ** 2) / 0.02)
+        f0 = (env * (1 + 0.3 * rng.uniform(size=(3, n, n))) * np.exp(2j * np.pi * 0.2 * rng.uniform(size=(3, n, n)))).astype(CT[bits])
+        area, wl, dz = 0.3, 532e-7, 0.4
+        b = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits, use_gpu=True, numpy_output=False)
+        c = Beam2D(area, n, wl, init_field=f0.copy(), complex_bits=bits, use_gpu=True, numpy_output=False)
+        lib = _lib.load()
+        b.propagate(dz); c.propagate(dz)                                   # (spectrum state and factor plane exist now)
+        l0 = lib.lp2d_launch_count()
+        _, M = b.propagate_sweep(dz, 3, probe=None, moments=True)
+        if n >= 256:                                                        # fused: one launch per step, no moments kernels
+            assert lib.lp2d_launch_count() - l0 in (3, 4), lib.lp2d_launch_count() - l0   # (+1: factor plane rebuilt by rows)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for k in range(3):
+            c.propagate(dz)
+            for i in range(3):
+                out = torch.zeros(5, dtype=torch.float64, device="cuda")
+                _lib.check(lib.lp2d_moments(_lib.C64 if bits == 64 else _lib.C128, c.field[i].contiguous().data_ptr(), n, float(c.dL), 0.0, 0.0,
+                                            out.data_ptr(), st), "moments")
+                m = out.cpu().numpy()
+                xc, yc = m[1] / m[0], m[2] / m[0]
+                d4 = 4 * np.sqrt([m[3] / m[0] - xc ** 2, m[4] / m[0] - yc ** 2])
+                assert np.allclose(M["centroid"][k][i], [xc, yc], rtol=1e-6, atol=1e-9 * area), (k, i)
+                assert np.allclose(M["D4sigma"][k][i], d4, rtol=1e-6), (k, i)
+                assert abs(xc - 0.11 * area) < 0.05 * area and abs(yc + 0.07 * area) < 0.05 * area   # x is the column coordinate
+    finally:
+        _b._PLAN_CACHE.clear()
