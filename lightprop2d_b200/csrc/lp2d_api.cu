@@ -833,7 +833,7 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         // transposed spectrum: a memory row is a grid COLUMN of the spectrum (factor rows by column), and the column
         // stage's transposed store lands the field in its natural orientation
         st[1].out_t = p->spectrum_t;
-        st[1].moments = moments; st[1].dL = dL;                 // (zeroed by the caller; the per-pass path below ignores them)
+        st[1].moments = moments; st[1].dL = dL;                 // (zeroed by the caller; inverse stage only; the per-pass path ignores them)
         const int rc = (p->spectrum_t || (p->fused_ops & 2)) ? run_p2<T>(p, st, 2, P2_FAC_H, p->spectrum_t, z, 0.0, batch, s, 2) : -1;
         if (rc >= 0) {
             if (moments_done != nullptr) *moments_done = (rc == 0 && moments != nullptr);

@@ -284,7 +284,7 @@ struct T3Cfg {
     static_assert(THREADS >= 32 && THREADS <= 1024, "block size");
 };
 
-template <typename T, int N, int E, int W, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV, bool OUT_T = false>
+template <typename T, int N, int E, int W, int HOOKS, int S, int AXIS, bool IN_RING, bool OUT_RING, bool MID, bool INV, bool OUT_T = false, bool MOM = false>
 __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<T>* xbuf, int tid, double (*s_mom)[5] = nullptr) {
     using K = T3Cfg<T, N, E, W>;
     constexpr int TPL = K::TPL;
@@ -395,7 +395,7 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
         }
         // Moment sums of the intensity, fused into the final stage: a z-sweep reads
         // centroid / D4sigma of every step without another pass over the field.  v[] holds the (unscaled) results.
-        if constexpr (AXIS == AX_COL && !OUT_RING && !MID) {
+        if constexpr (MOM && AXIS == AX_COL && !OUT_RING && !MID) {
             if (st.moments != nullptr && s_mom != nullptr) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;                        // sums over the thread's positions along the line
 #pragma unroll
@@ -605,6 +605,8 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
             else t3_item<T, N, E, W, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
         } else if (it.s == 1) {
             if (p.st[1].mid) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
+            else if (p.st[1].moments != nullptr && p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true, true>(p, it, xbuf, tid, s_mom);
+            else if (p.st[1].moments != nullptr) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, false, true>(p, it, xbuf, tid, s_mom);
             else if (p.st[1].out_t && p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true>(p, it, xbuf, tid, s_mom);
             else if (p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false, true>(p, it, xbuf, tid, s_mom);
             else if (p.use_tma && p.st[1].inverse) t3_col_tma_item<T, N, E, W, true>(p, it, xbuf, &s_bar, tma_parity, tid);
