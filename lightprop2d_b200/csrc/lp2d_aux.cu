@@ -254,6 +254,78 @@ __global__ void __launch_bounds__(256) modes_project_kernel(const cx<T>* __restr
     }
 }
 
+// Tiled complex128 projection (the tensor cores have no FP64 path worth a 3-term split here): a register-tiled GEMM
+// C[b][m] += sum_k F[b][crop(k)] * M[m][k] over a slice of k.  CTA = 4 warps: a warp owns 32 consecutive modes x MT
+// (mode tm + 32 i) and BT beams, so a k step costs MT conflict-free + BT broadcast shared-memory loads for MT*BT
+// complex FMAs (4 DFMA each) -- the FP64 pipe, not memory, bounds it (8*Bt*M*K flop against (M + Bt)*K*16 bytes:
+// 7.5 flop/byte at 16 beams).  The mode matrix is read ONCE per 16 beams (the one-mode-per-CTA kernel above re-reads
+// every field sample once per mode through L2: 5.6 ms at 256 modes x 512^2 x 16 beams, profiles/r3h_*).  k is split
+// over gridDim.z CTAs; partial sums are added with FP64 atomics into the zeroed coefficient array.
+template <int MT, int BT, int KC>
+__global__ void __launch_bounds__(128) modes_project_f64_kernel(const double2* __restrict__ field, const double2* __restrict__ modes,
+                                                                double2* __restrict__ coeffs, int n, int nb, int nmodes, long long batch,
+                                                                int kslice) {
+    constexpr int MTILE = 32 * MT, BTILE = 4 * BT;
+    __shared__ double2 Ms[KC][MTILE + 1];
+    __shared__ double2 Fs[KC][BTILE];
+    const int tid = threadIdx.x, tm = tid & 31, tb = tid >> 5;
+    const int m0 = blockIdx.x * MTILE;
+    const long long b0 = (long long)blockIdx.y * BTILE;
+    const long long kk = (long long)nb * nb;
+    const long long k_begin = (long long)blockIdx.z * kslice;
+    const long long k_end = (k_begin + kslice < kk) ? k_begin + kslice : kk;
+    const int dn = (n - nb) / 2;
+    const long long plane = (long long)n * n;
+    double2 acc[MT][BT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < BT; ++j) acc[i][j] = make_double2(0.0, 0.0);
+    for (long long k0 = k_begin; k0 < k_end; k0 += KC) {                // (KC divides nb and kslice: a chunk lies in one crop row)
+        __syncthreads();
+        // modes tile: MTILE rows of KC consecutive samples, stored transposed
+        for (int q = tid; q < MTILE * KC; q += 128) {
+            const int m = q / KC, kq = q % KC;
+            Ms[kq][m] = (m0 + m < nmodes) ? __ldcs(&modes[(long long)(m0 + m) * kk + k0 + kq]) : make_double2(0.0, 0.0);
+        }
+        const int r = (int)(k0 / nb), c = (int)(k0 % nb);
+        const long long off = (long long)(r + dn) * n + (c + dn);
+        for (int q = tid; q < BTILE * KC; q += 128) {
+            const int b = q / KC, kq = q % KC;
+            Fs[kq][b] = (b0 + b < batch) ? field[(b0 + b) * plane + off + kq] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kq = 0; kq < KC; ++kq) {
+            double2 mv[MT], fv[BT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) mv[i] = Ms[kq][tm + 32 * i];
+#pragma unroll
+            for (int j = 0; j < BT; ++j) fv[j] = Fs[kq][tb * BT + j];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < BT; ++j) {
+                    acc[i][j].x += mv[i].x * fv[j].x - mv[i].y * fv[j].y;
+                    acc[i][j].y += mv[i].x * fv[j].y + mv[i].y * fv[j].x;
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int m = m0 + tm + 32 * i;
+#pragma unroll
+        for (int j = 0; j < BT; ++j) {
+            const long long b = b0 + tb * BT + j;
+            if (m < nmodes && b < batch) {
+                double* dst = reinterpret_cast<double*>(&coeffs[b * nmodes + m]);
+                atomicAdd(dst, acc[i][j].x);
+                atomicAdd(dst + 1, acc[i][j].y);
+            }
+        }
+    }
+}
+
 // Flat form for a strip of the crop (a slab of a grid decomposed over several GPUs): coeffs[k] = sum_{p < K}
 // modes[k * ldm + p] * f[p]; the partial sums of the ranks are added by the caller (one all-reduce).
 template <typename T>
@@ -461,6 +533,26 @@ int lp2d_modes_project(int dtype, const void* field, const void* modes, void* co
             if (rc != LP2D_EUNSUPPORTED) return rc;
         }
     }
+    if (dtype == LP2D_C128 && nb % 16 == 0) {
+        // register-tiled FP64 GEMM, k split so that the grid fills the GPU a few times over; up to 4 beams: one beam
+        // per warp (the call is a matrix-vector product bound by the read of the mode matrix)
+        constexpr int MT = 4, KC = 16;
+        const int btt = batch <= 4 ? 1 : 4;
+        const long long kk = (long long)nb * nb;
+        const unsigned gx = (unsigned)((nmodes + 32 * MT - 1) / (32 * MT)), gy = (unsigned)((batch + 4 * btt - 1) / (4 * btt));
+        long long splits = (148ll * 4 + (long long)gx * gy - 1) / ((long long)gx * gy);
+        long long kslice = ((kk + splits - 1) / splits + KC - 1) / KC * KC;
+        if (kslice < 4 * KC) kslice = 4 * KC;
+        splits = (kk + kslice - 1) / kslice;
+        cudaError_t e = cudaMemsetAsync(coeffs, 0, (size_t)batch * nmodes * sizeof(double2), s);
+        if (e != cudaSuccess) return set_error(LP2D_ECUDA, std::string("modes_project memset: ") + cudaGetErrorString(e));
+        const dim3 grid(gx, gy, (unsigned)splits);
+        if (btt == 1)
+            modes_project_f64_kernel<MT, 1, KC><<<grid, 128, 0, s>>>((const double2*)field, (const double2*)modes, (double2*)coeffs, n, nb, nmodes, batch, (int)kslice);
+        else
+            modes_project_f64_kernel<MT, 4, KC><<<grid, 128, 0, s>>>((const double2*)field, (const double2*)modes, (double2*)coeffs, n, nb, nmodes, batch, (int)kslice);
+        return done("modes_project (tiled FP64) launch");
+    }
     constexpr int BT = 8;
     dim3 grid((unsigned)nmodes, (unsigned)((batch + BT - 1) / BT));
     if (dtype == LP2D_C64)
@@ -502,6 +594,12 @@ int lp2d_modes_synthesize(int dtype, const void* coeffs, const void* modes, void
         constexpr int BT = 8;
         dim3 grid(gx, (unsigned)((batch + BT - 1) / BT));
         modes_synthesize_kernel<float, BT, 128><<<grid, 256, 0, s>>>((const float2*)coeffs, (const float2*)modes, (float2*)field, n, nb, nmodes, batch);
+    } else if (batch > 4) {
+        // 16 beams per thread: the mode matrix (the big operand) is read once per 16 beams (4: 4.3 GB of DRAM reads
+        // for 1.07 GB of modes at 256 modes x 512^2 x 16 beams, profiles/r3h_*)
+        constexpr int BT = 16;
+        dim3 grid(gx, (unsigned)((batch + BT - 1) / BT));
+        modes_synthesize_kernel<double, BT, 64><<<grid, 256, 0, s>>>((const double2*)coeffs, (const double2*)modes, (double2*)field, n, nb, nmodes, batch);
     } else {
         constexpr int BT = 4;
         dim3 grid(gx, (unsigned)((batch + BT - 1) / BT));
