@@ -93,6 +93,7 @@ struct lp2d_plan {
     void* tw;          // device twiddles (cx<T>)
     double* tabs;      // device: a | b | x2, n doubles each
     long long chunk_bytes;   // intermediate kept per kernel pair (L2 residency)
+    bool chunk_explicit;     // LP2D_CHUNK_MB was given: no automatic whole-batch passes for large planes
     int h_groups;            // beam slabs one CTA of the H row pass walks over
     int hints;               // use evict-first accesses for streaming data
     int nstreams;            // auxiliary streams the chunks are fanned out over
@@ -212,6 +213,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     p->tw = nullptr; p->tabs = nullptr;
     const char* env = getenv("LP2D_CHUNK_MB");
     p->chunk_bytes = (env ? atoll(env) : 32) * (1ll << 20);
+    p->chunk_explicit = env != nullptr;
     if (p->chunk_bytes <= 0) p->chunk_bytes = 1ll << 62;
     env = getenv("LP2D_HGROUPS");
     p->h_groups = env ? atoi(env) : 8;
@@ -706,6 +708,10 @@ template <typename T>
 long long chunk_beams(const lp2d_plan* p, long long batch) {
     const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
     long long c = p->chunk_bytes / plane;
+    // Planes of 16 MB and more (complex128 from 1024 points, complex64 from 2048): a chunk would be one or two beams,
+    // i.e. launches of one or two waves fanned out over streams that then compete for L2; the whole batch per pass is
+    // 13-24 % faster there (profiles/r3k_sweep_perpass_sizes.log: 4096^2 complex64 239 -> 181 us per beam)
+    if (c < 4 && !p->chunk_explicit) c = batch;
     if (c < 1) c = 1;
     // keep the row-count of a launch inside int range
     const long long cap = (long long)(0x7fffffff) / p->n;
