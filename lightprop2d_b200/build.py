@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "liblp2d.so")
-UNITS = ["lp2d_api.cu", "lp2d_aux.cu", "lp2d_f32.cu", "lp2d_f64.cu", "lp2d_p2_f32.cu", "lp2d_p2_f64.cu", "lp2d_modes_tc.cu", "lp2d_xl.cu", "lp2d_generic.cu", "lp2d_gen.cu"]
+UNITS = ["lp2d_api.cu", "lp2d_aux.cu", "lp2d_f32.cu", "lp2d_f64.cu", "lp2d_p2_f32.cu", "lp2d_p2_f64.cu", "lp2d_modes_tc.cu", "lp2d_xl.cu", "lp2d_generic.cu", "lp2d_gen.cu", "lp2d_colstep.cu"]
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # tuning builds only: extra -D definitions (LP2D_Q4_CLOCKS=1 phase clocks, LP2D_ABLATION=1 no-transform variants)

@@ -9,6 +9,7 @@
 #include "../../include/lp2d.h"
 #include "dispatch.h"
 #include "pipe2_ops.cuh"
+#include "colstep.cuh"
 #include "xl_line.cuh"
 
 
@@ -122,6 +123,16 @@ struct lp2d_plan {
     int q4_ctas;               // resident CTAs per SM (1)
     int q4_lag;                // tuning override (0 = automatic)
     unsigned long long* q4_timing;   // tuning aid: phase clocks of the persistent form (LP2D_Q4_TIMING=1), else NULL
+    // long columns in two steps (colstep.cuh): column length n = cs_a * cs_b; 0 = the one-kernel column pass
+    int cs_a, cs_b;
+    const ColStepOps<float>* cs32[2];
+    const ColStepOps<double>* cs64[2];
+    void* cs_tw[2];            // twiddles of the two short-line plans
+    void* cs_tw4;              // exp(-2 pi i q / n), q < n
+    void* cs_scratch;          // intermediate of the two steps (allocated on first use)
+    size_t cs_scratch_bytes;
+    int cs_ctas[2];
+    int cs_sms;
     int spectrum_t;            // spectra of this plan are stored TRANSPOSED (lp2d_plan_set_spectrum_layout)
     int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
@@ -266,6 +277,8 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
     p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr; p->spectrum_t = 0;
+    p->cs_a = p->cs_b = 0; p->cs32[0] = p->cs32[1] = nullptr; p->cs64[0] = p->cs64[1] = nullptr;
+    p->cs_tw[0] = p->cs_tw[1] = nullptr; p->cs_tw4 = nullptr; p->cs_scratch = nullptr; p->cs_scratch_bytes = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
     // the fused step kernel is the default wherever an instance exists (LP2D_PIPE=0: one kernel per pass)
     env = getenv("LP2D_PIPE");
@@ -334,6 +347,62 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             env = getenv("LP2D_Q4_TIMING");
             if (env && atoi(env) != 0 && cudaMalloc(&p->q4_timing, 16 * sizeof(unsigned long long)) == cudaSuccess)
                 cudaMemset(p->q4_timing, 0, 16 * sizeof(unsigned long long));
+        }
+    }
+    // Long columns in two steps (colstep.cuh) where the one-kernel column pass works on 32-byte pieces AND the two
+    // streaming steps (4 P B instead of 2 P B) still win: 4096 complex128 (398 -> 372 us per beam) and 8192 complex64
+    // (996 -> 819); not 2048 complex128 (83 -> 87) or 4096 complex64 (181 -> 184), profiles/r3n_colstep.log.
+    // LP2D_COLSTEP=0 / 1 forces it off / on (1: from 1024 points)
+    {
+        const SizeOps<float>* c32 = p->ops32;
+        const SizeOps<double>* c64 = p->ops64;
+        const int wbytes = c32 ? c32->w_col * 8 : (c64 ? c64->w_col * 16 : 1 << 20);
+        env = getenv("LP2D_COLSTEP");
+        const bool want = env ? (atoi(env) != 0 && n >= 1024) : (wbytes < 64 && n * (dtype == LP2D_C64 ? 8 : 16) >= 65536);
+        if (want && (c32 != nullptr || c64 != nullptr) && n >= 1024 && n <= 16384) {
+            int a = 32;
+            while (a * a < n) a *= 2;                       // a * b = n, a <= b <= 2 a: 1024 = 32 x 32 ... 8192 = 64 x 128
+            int b = n / a;
+            if (a > b) { const int t = a; a = b; b = t; }
+            const int len[2] = {a, b};
+            bool ok = true;
+            for (int i = 0; i < 2 && ok; ++i) {
+                if (dtype == LP2D_C64) { p->cs32[i] = find_colstep_f32(len[i]); ok = p->cs32[i] != nullptr && p->cs32[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
+                else { p->cs64[i] = find_colstep_f64(len[i]); ok = p->cs64[i] != nullptr && p->cs64[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
+                if (ok && p->cs_ctas[i] < 1) ok = false;
+            }
+            const size_t csz = dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2);
+            auto upload = [&](const std::vector<double>& w, void** dst) -> bool {
+                const size_t cnt = w.size() / 2;
+                if (cudaMalloc(dst, (cnt ? cnt : 1) * csz) != cudaSuccess) return false;
+                if (cnt == 0) return true;
+                if (dtype == LP2D_C64) {
+                    std::vector<float> wf(w.size());
+                    for (size_t i = 0; i < w.size(); ++i) wf[i] = (float)w[i];
+                    return cudaMemcpy(*dst, wf.data(), cnt * csz, cudaMemcpyHostToDevice) == cudaSuccess;
+                }
+                return cudaMemcpy(*dst, w.data(), cnt * csz, cudaMemcpyHostToDevice) == cudaSuccess;
+            };
+            for (int i = 0; i < 2 && ok; ++i) {
+                std::vector<double> w;
+                if (dtype == LP2D_C64) p->cs32[i]->twiddles(w); else p->cs64[i]->twiddles(w);
+                ok = upload(w, &p->cs_tw[i]);
+            }
+            if (ok) {
+                std::vector<double> w(2 * (size_t)n);
+                const long double two_pi = 6.283185307179586476925286766559005768L;
+                for (int q = 0; q < n; ++q) {
+                    const long double ang = -two_pi * (long double)q / (long double)n;
+                    w[2 * (size_t)q] = (double)cosl(ang);
+                    w[2 * (size_t)q + 1] = (double)sinl(ang);
+                }
+                ok = upload(w, &p->cs_tw4);
+            }
+            int dev = 0;
+            p->cs_sms = 148;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&p->cs_sms, cudaDevAttrMultiProcessorCount, dev);
+            if (ok) { p->cs_a = a; p->cs_b = b; }
+            else { cudaGetLastError(); p->cs_a = p->cs_b = 0; }
         }
     }
     env = getenv("LP2D_PIPE_G");     p->pipe_g = env ? atoi(env) : 0;
@@ -420,6 +489,7 @@ int lp2d_q4_timing(lp2d_plan* p, unsigned long long* host16, int reset) {
 int lp2d_plan_destroy(lp2d_plan* p) {
     if (p == nullptr) return LP2D_OK;
     cudaFree(p->q4_timing);
+    cudaFree(p->cs_tw[0]); cudaFree(p->cs_tw[1]); cudaFree(p->cs_tw4); cudaFree(p->cs_scratch);
     cudaFree(p->tw);
     cudaFree(p->tabs);
     cudaFree(p->ring);
@@ -759,8 +829,68 @@ int rows(const lp2d_plan* p, int pre, LineArgs<T> a, long long beams, cudaStream
     LP2D_CU(ops_of<T>(p)->row(pre, a, s), "row pass launch");
     return LP2D_OK;
 }
+template <typename T> const ColStepOps<T>* cs_of(const lp2d_plan* p, int i);
+template <> const ColStepOps<float>* cs_of<float>(const lp2d_plan* p, int i) { return p->cs32[i]; }
+template <> const ColStepOps<double>* cs_of<double>(const lp2d_plan* p, int i) { return p->cs64[i]; }
+
+// The column pass in two steps (colstep.cuh): in -> scratch (transforms of length cs_a over rows cs_b apart, twiddle),
+// scratch -> out (transforms of length cs_b over consecutive rows, result rows cs_a apart).  in may be out.
+template <typename T>
+int cols_two_step(lp2d_plan* p, const LineArgs<T>& a, long long beams, cudaStream_t s) {
+    const long long n = p->n, plane = n * n;
+    const size_t plane_bytes = (size_t)plane * sizeof(cx<T>);
+    // scratch: as many planes as fit 1 GiB (at least one), allocated on first use and kept
+    long long chunk = (long long)((1ull << 30) / plane_bytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > beams) chunk = beams;
+    if (p->cs_scratch_bytes < (size_t)chunk * plane_bytes) {
+        if (p->cs_scratch != nullptr) { LP2D_CU(cudaStreamSynchronize(s), "column scratch: synchronise"); cudaFree(p->cs_scratch); p->cs_scratch = nullptr; p->cs_scratch_bytes = 0; }
+        LP2D_CU(cudaMalloc(&p->cs_scratch, (size_t)chunk * plane_bytes), "cudaMalloc(column scratch)");
+        p->cs_scratch_bytes = (size_t)chunk * plane_bytes;
+    }
+    const bool inv = (a.flags & F_INVERSE) != 0;
+    const int A = p->cs_a, B = p->cs_b;
+    for (long long b0 = 0; b0 < beams; b0 += chunk) {
+        const long long nb = beams - b0 < chunk ? beams - b0 : chunk;
+        for (int step = 0; step < 2; ++step) {
+            const ColStepOps<T>* ops = cs_of<T>(p, step);
+            ColStepArgs<T> c;
+            memset(&c, 0, sizeof c);
+            c.tw = static_cast<const cx<T>*>(p->cs_tw[step]);
+            c.tiles = (int)(n / ops->wc);
+            c.scale = (T)1;
+            if (step == 0) {
+                c.in = a.in + b0 * a.beam_stride; c.in_plane = a.beam_stride;
+                c.out = static_cast<cx<T>*>(p->cs_scratch); c.out_plane = plane;
+                c.tw4 = static_cast<const cx<T>*>(p->cs_tw4);
+                c.U = B;                                     // u = j2
+                c.in_u = n; c.in_pos = (long long)B * n;     // row j1 * B + j2
+                c.out_u = n; c.out_pos = (long long)B * n;   // (k1, j2) -> row k1 * B + j2
+                c.swap_in = inv ? 1 : 0;
+            } else {
+                c.in = static_cast<const cx<T>*>(p->cs_scratch); c.in_plane = plane;
+                c.out = a.out ? a.out + b0 * a.beam_stride : nullptr; c.out_plane = a.beam_stride;
+                c.inten = a.inten ? a.inten + b0 * a.beam_stride : nullptr;
+                c.U = A;                                     // u = k1
+                c.in_u = (long long)B * n; c.in_pos = n;     // row k1 * B + j2
+                c.out_u = n; c.out_pos = (long long)A * n;   // k = k1 + A * k2
+                c.swap_out = inv ? 1 : 0;
+                c.scale = a.scale;
+                c.stream_out = (a.flags & F_OUT_STREAM) ? 1 : 0;
+            }
+            c.nitems = nb * c.U * c.tiles;
+            long long grid = (long long)p->cs_sms * p->cs_ctas[step] * 4;
+            if (grid > c.nitems) grid = c.nitems;
+            LP2D_CU(ops->launch(c, (unsigned)grid, s), "two-step column pass launch");
+        }
+    }
+    return LP2D_OK;
+}
+
 template <typename T>
 int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream_t s) {
+    if (mid == MID_NONE && p->cs_a != 0 && a.out_pre == nullptr && a.mask_kind == MASK_NONE)
+        return cols_two_step<T>(const_cast<lp2d_plan*>(p), a, beams, s);
     a.groups = 1;
     a.group_beams = beams;
     a.nbeams = beams;

@@ -1136,3 +1136,37 @@ def test_fused_moment_sums_in_sweep(bits, n, layout_t, monkeypatch):
                 assert abs(xc - 0.11 * area) < 0.05 * area and abs(yc + 0.07 * area) < 0.05 * area   # x is the column coordinate
     finally:
         _b._PLAN_CACHE.clear()
+
+
+@pytest.mark.parametrize("bits,n", [(64, 1024), (128, 1024), (64, 2048), (128, 2048)])
+def test_two_step_column_pass_equals_one_kernel_pass(bits, n, monkeypatch):
+    """LP2D_COLSTEP=1: the column pass as two short-line kernels (colstep.cuh; default from 4096 complex128 / 8192
+    complex64, covered at those sizes by test_oracle_large_sizes) against the one-kernel column pass: fft2, inverse
+    with |E|^2, in place and out of place, ragged batch -- same values up to rounding."""
+    from lightprop2d_b200 import beam2d as _b
+    lib = _lib.load()
+    batch = 3
+    ct = torch.complex64 if bits == 64 else torch.complex128
+    torch.manual_seed(3)
+    f = torch.randn(batch, n, n, dtype=ct, device="cuda")
+    res = {}
+    for cs in ("0", "1"):
+        monkeypatch.setenv("LP2D_COLSTEP", cs)
+        monkeypatch.setenv("LP2D_PIPE", "0")
+        _b._PLAN_CACHE.clear()
+        b = Beam2D(0.4 * n / 1024, n, 532e-7, init_field=f[:1], complex_bits=bits, use_gpu=True)
+        plan = b._plan.handle
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        s = torch.empty_like(f); o = torch.empty_like(f)
+        inten = torch.empty(batch, n, n, dtype=torch.float32 if bits == 64 else torch.float64, device="cuda")
+        _lib.check(lib.lp2d_fft2(plan, f.data_ptr(), s.data_ptr(), batch, 0, st), "fft2")
+        spec = s.clone()
+        _lib.check(lib.lp2d_propagate(plan, s.data_ptr(), o.data_ptr(), inten.data_ptr(), batch, 0.02, st), "propagate")
+        g = f.clone()
+        _lib.check(lib.lp2d_pass(plan, _lib.AXIS_COLS, _lib.OP_FFT, g.data_ptr(), g.data_ptr(), None, None, batch, 1, 0.0, st), "pass")
+        res[cs] = (spec.cpu().numpy(), o.cpu().numpy(), inten.cpu().numpy(), g.cpu().numpy())
+    _b._PLAN_CACHE.clear()
+    tol = 2e-6 if bits == 64 else 1e-14
+    for x, y in zip(res["0"], res["1"]):
+        assert rel_l2(y, x) <= tol
+    assert not np.array_equal(res["0"][0], res["1"][0])          # (the two paths really are different kernels)
