@@ -133,6 +133,7 @@ struct lp2d_plan {
     size_t cs_scratch_bytes;
     int cs_ctas[2];
     int cs_sms;
+    int cs_panel_mb;           // column panel whose scratch stays in L2 between the two steps (0: whole planes)
     int spectrum_t;            // spectra of this plan are stored TRANSPOSED (lp2d_plan_set_spectrum_layout)
     int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
@@ -401,6 +402,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             int dev = 0;
             p->cs_sms = 148;
             if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&p->cs_sms, cudaDevAttrMultiProcessorCount, dev);
+            env = getenv("LP2D_COLSTEP_PANEL_MB"); p->cs_panel_mb = env ? atoi(env) : 0;       // (panels measured slower: launches of a few microseconds, profiles/r3o_colstep_panels.log)
             if (ok) { p->cs_a = a; p->cs_b = b; }
             else { cudaGetLastError(); p->cs_a = p->cs_b = 0; }
         }
@@ -838,50 +840,57 @@ template <> const ColStepOps<double>* cs_of<double>(const lp2d_plan* p, int i) {
 template <typename T>
 int cols_two_step(lp2d_plan* p, const LineArgs<T>& a, long long beams, cudaStream_t s) {
     const long long n = p->n, plane = n * n;
-    const size_t plane_bytes = (size_t)plane * sizeof(cx<T>);
-    // scratch: as many planes as fit 1 GiB (at least one), allocated on first use and kept
-    long long chunk = (long long)((1ull << 30) / plane_bytes);
-    if (chunk < 1) chunk = 1;
-    if (chunk > beams) chunk = beams;
-    if (p->cs_scratch_bytes < (size_t)chunk * plane_bytes) {
+    // One beam at a time through a scratch of one plane (default), or one PANEL of columns at a time
+    // (LP2D_COLSTEP_PANEL_MB > 0): the scratch of a panel (n rows x wp columns) is then written by step 1 and read by
+    // step 2 while it is still in L2, so the pass moves 2 P B through HBM like the one-kernel pass -- but in launches of
+    // a few microseconds each, which measured slower at every size (profiles/r3o_colstep_panels.log).
+    const long long panel_bytes = (long long)p->cs_panel_mb << 20;
+    long long wp = panel_bytes > 0 ? panel_bytes / (n * (long long)sizeof(cx<T>)) : n;
+    const int wc = cs_of<T>(p, 0)->wc;
+    if (wp > n) wp = n;
+    if (wp < wc) wp = wc;
+    while (wp & (wp - 1)) wp &= wp - 1;                      // power of two: divides n, multiple of the tile width
+    const size_t need = (size_t)n * wp * sizeof(cx<T>);
+    if (p->cs_scratch_bytes < need) {
         if (p->cs_scratch != nullptr) { LP2D_CU(cudaStreamSynchronize(s), "column scratch: synchronise"); cudaFree(p->cs_scratch); p->cs_scratch = nullptr; p->cs_scratch_bytes = 0; }
-        LP2D_CU(cudaMalloc(&p->cs_scratch, (size_t)chunk * plane_bytes), "cudaMalloc(column scratch)");
-        p->cs_scratch_bytes = (size_t)chunk * plane_bytes;
+        LP2D_CU(cudaMalloc(&p->cs_scratch, need), "cudaMalloc(column scratch)");
+        p->cs_scratch_bytes = need;
     }
     const bool inv = (a.flags & F_INVERSE) != 0;
     const int A = p->cs_a, B = p->cs_b;
-    for (long long b0 = 0; b0 < beams; b0 += chunk) {
-        const long long nb = beams - b0 < chunk ? beams - b0 : chunk;
-        for (int step = 0; step < 2; ++step) {
-            const ColStepOps<T>* ops = cs_of<T>(p, step);
-            ColStepArgs<T> c;
-            memset(&c, 0, sizeof c);
-            c.tw = static_cast<const cx<T>*>(p->cs_tw[step]);
-            c.tiles = (int)(n / ops->wc);
-            c.scale = (T)1;
-            if (step == 0) {
-                c.in = a.in + b0 * a.beam_stride; c.in_plane = a.beam_stride;
-                c.out = static_cast<cx<T>*>(p->cs_scratch); c.out_plane = plane;
-                c.tw4 = static_cast<const cx<T>*>(p->cs_tw4);
-                c.U = B;                                     // u = j2
-                c.in_u = n; c.in_pos = (long long)B * n;     // row j1 * B + j2
-                c.out_u = n; c.out_pos = (long long)B * n;   // (k1, j2) -> row k1 * B + j2
-                c.swap_in = inv ? 1 : 0;
-            } else {
-                c.in = static_cast<const cx<T>*>(p->cs_scratch); c.in_plane = plane;
-                c.out = a.out ? a.out + b0 * a.beam_stride : nullptr; c.out_plane = a.beam_stride;
-                c.inten = a.inten ? a.inten + b0 * a.beam_stride : nullptr;
-                c.U = A;                                     // u = k1
-                c.in_u = (long long)B * n; c.in_pos = n;     // row k1 * B + j2
-                c.out_u = n; c.out_pos = (long long)A * n;   // k = k1 + A * k2
-                c.swap_out = inv ? 1 : 0;
-                c.scale = a.scale;
-                c.stream_out = (a.flags & F_OUT_STREAM) ? 1 : 0;
+    for (long long b0 = 0; b0 < beams; ++b0) {
+        for (long long c0 = 0; c0 < n; c0 += wp) {
+            for (int step = 0; step < 2; ++step) {
+                const ColStepOps<T>* ops = cs_of<T>(p, step);
+                ColStepArgs<T> c;
+                memset(&c, 0, sizeof c);
+                c.tw = static_cast<const cx<T>*>(p->cs_tw[step]);
+                c.tiles = (int)(wp / ops->wc);
+                c.scale = (T)1;
+                if (step == 0) {
+                    c.in = a.in + b0 * a.beam_stride + c0; c.in_plane = a.beam_stride;
+                    c.out = static_cast<cx<T>*>(p->cs_scratch); c.out_plane = n * wp;
+                    c.tw4 = static_cast<const cx<T>*>(p->cs_tw4);
+                    c.U = B;                                       // u = j2
+                    c.in_u = n; c.in_pos = (long long)B * n;       // row j1 * B + j2 of the grid
+                    c.out_u = wp; c.out_pos = (long long)B * wp;   // (k1, j2) -> row k1 * B + j2 of the panel
+                    c.swap_in = inv ? 1 : 0;
+                } else {
+                    c.in = static_cast<const cx<T>*>(p->cs_scratch); c.in_plane = n * wp;
+                    c.out = a.out ? a.out + b0 * a.beam_stride + c0 : nullptr; c.out_plane = a.beam_stride;
+                    c.inten = a.inten ? a.inten + b0 * a.beam_stride + c0 : nullptr;
+                    c.U = A;                                       // u = k1
+                    c.in_u = (long long)B * wp; c.in_pos = wp;     // row k1 * B + j2 of the panel
+                    c.out_u = n; c.out_pos = (long long)A * n;     // k = k1 + A * k2
+                    c.swap_out = inv ? 1 : 0;
+                    c.scale = a.scale;
+                    c.stream_out = (a.flags & F_OUT_STREAM) ? 1 : 0;
+                }
+                c.nitems = (long long)c.U * c.tiles;
+                long long grid = (long long)p->cs_sms * p->cs_ctas[step] * 4;
+                if (grid > c.nitems) grid = c.nitems;
+                LP2D_CU(ops->launch(c, (unsigned)grid, s), "two-step column pass launch");
             }
-            c.nitems = nb * c.U * c.tiles;
-            long long grid = (long long)p->cs_sms * p->cs_ctas[step] * 4;
-            if (grid > c.nitems) grid = c.nitems;
-            LP2D_CU(ops->launch(c, (unsigned)grid, s), "two-step column pass launch");
         }
     }
     return LP2D_OK;
