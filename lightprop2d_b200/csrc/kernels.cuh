@@ -23,7 +23,10 @@
 namespace lp2d {
 
 enum { AX_ROW = 0, AX_COL = 1 };
-enum { PRE_NONE = 0, PRE_LENS = 1, PRE_H = 2 };
+// PRE_HPLANE: the transfer function is read from a plane the host has built once for this z (factor_plane_kernel, folded by
+// the kx -> -kx symmetry) instead of being evaluated in FP64 per sample: a z-sweep with a constant step, single field,
+// spends a quarter of its row pass on sqrt / sincospi otherwise (profiles/r3s_h_cost.log)
+enum { PRE_NONE = 0, PRE_LENS = 1, PRE_H = 2, PRE_HPLANE = 3 };
 enum { MID_NONE = 0, MID_H = 1 };
 enum { F_INVERSE = 1,
        F_IN_STREAM = 2,     // input is read once: evict-first loads
@@ -49,6 +52,8 @@ struct LineArgs {
     const double* a_tab;    // k0^2 - Kx[i]^2
     const double* b_tab;    // Ky[j]^2
     const double* x2_tab;   // X[i]^2
+    const cx<T>* fac;       // PRE_HPLANE: H plane [row j][idx = min(i, N - i)], row stride fac_stride
+    int fac_stride;
     double z;               // propagation distance
     double lens_k0;         // 1 / wl
     double lens_2f;         // 2 * f
@@ -248,6 +253,14 @@ line_kernel(const LineArgs<T> p) {
         if constexpr (PRE == PRE_H) {
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = cmul(v[m], sH[t + TPL * m]);
+        }
+        if constexpr (PRE == PRE_HPLANE && AXIS == AX_ROW) {
+            const cx<T>* frow = p.fac + (long long)fixed * p.fac_stride;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int pos = t + TPL * m;
+                v[m] = cmul(v[m], __ldg(frow + (pos <= N / 2 ? pos : N - pos)));
+            }
         }
         if (p.out_pre != nullptr && active) {
 #pragma unroll

@@ -134,6 +134,11 @@ struct lp2d_plan {
     int cs_ctas[2];
     int cs_sms;
     int cs_panel_mb;           // column panel whose scratch stays in L2 between the two steps (0: whole planes)
+    // one-kernel-per-pass path: H plane of a repeated step (z-sweeps): built when a z comes a second time in a row
+    void* hp_fac;              // [n][n/2 + 2], allocated on first use
+    double hp_z, hp_seen_z;    // z the plane holds / z of the previous stateful call
+    bool hp_valid, hp_seen;
+    int hp_mode;               // LP2D_HPLANE: 0 never, 1 automatic (default), 2 always
     int spectrum_t;            // spectra of this plan are stored TRANSPOSED (lp2d_plan_set_spectrum_layout)
     int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
@@ -278,6 +283,8 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
     p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr; p->spectrum_t = 0;
+    p->hp_fac = nullptr; p->hp_z = 0; p->hp_seen_z = 0; p->hp_valid = false; p->hp_seen = false;
+    env = getenv("LP2D_HPLANE"); p->hp_mode = env ? atoi(env) : 1;
     p->cs_a = p->cs_b = 0; p->cs32[0] = p->cs32[1] = nullptr; p->cs64[0] = p->cs64[1] = nullptr;
     p->cs_tw[0] = p->cs_tw[1] = nullptr; p->cs_tw4 = nullptr; p->cs_scratch = nullptr; p->cs_scratch_bytes = 0;
     p->p2_32 = nullptr; p->p2_64 = nullptr; p->p2_tw = nullptr; p->p2_fac = nullptr; p->fac_kind = 0; p->p2_done = nullptr; p->p2_used = false; p->p2_stream = nullptr;
@@ -491,6 +498,7 @@ int lp2d_q4_timing(lp2d_plan* p, unsigned long long* host16, int reset) {
 int lp2d_plan_destroy(lp2d_plan* p) {
     if (p == nullptr) return LP2D_OK;
     cudaFree(p->q4_timing);
+    cudaFree(p->hp_fac);
     cudaFree(p->cs_tw[0]); cudaFree(p->cs_tw[1]); cudaFree(p->cs_tw4); cudaFree(p->cs_scratch);
     cudaFree(p->tw);
     cudaFree(p->tabs);
@@ -989,6 +997,25 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
     const long long plane = (long long)p->n * p->n;
     const long long cb = chunk_beams<T>(p, batch);
     const int H = p->hints;
+    // The H plane of a repeated step: the second consecutive call with the same z builds it (FP64, reference operation
+    // order, half the samples by the kx fold), later calls read it -- the per-sample evaluation costs a single-field row
+    // pass 17-25 % of the whole step (profiles/r3s_h_cost.log).  Needs even tables (the fold).
+    bool use_plane = false;
+    if (p->hp_mode != 0 && p->h_even) {
+        if (p->hp_valid && p->hp_z == z) use_plane = true;
+        else if (p->hp_mode == 2 || (p->hp_seen && p->hp_seen_z == z)) {
+            const int fl = p->n / 2 + 2;
+            if (p->hp_fac == nullptr && cudaMalloc(&p->hp_fac, (size_t)p->n * fl * sizeof(cx<T>)) != cudaSuccess) { cudaGetLastError(); p->hp_fac = nullptr; }
+            if (p->hp_fac != nullptr) {
+                cudaError_t e = sizeof(T) == 4
+                    ? p2_factor_plane_f32(static_cast<float2*>(p->hp_fac), p->tabs, p->n, fl, P2_FAC_H, 0, 0, z, 0.0, 0.0, s)
+                    : p2_factor_plane_f64(static_cast<double2*>(p->hp_fac), p->tabs, p->n, fl, P2_FAC_H, 0, 0, z, 0.0, 0.0, s);
+                if (e != cudaSuccess) return cuda_fail(e, "H plane launch");
+                p->hp_valid = true; p->hp_z = z; use_plane = true;
+            }
+        }
+        p->hp_seen = true; p->hp_seen_z = z;
+    }
     Fan fan(p, s, (batch + cb - 1) / cb);
     LP2D_CU(fan.fork(), "stream fork");
     for (long long b0 = 0; b0 < batch; b0 += cb) {
@@ -1000,7 +1027,8 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         a.out_pre = static_cast<cx<T>*>(spectrum) + b0 * plane;
         a.out = static_cast<cx<T>*>(field) + b0 * plane;
         a.flags = F_INVERSE | (H ? (F_IN_STREAM | F_STATE_STREAM) : 0); a.scale = sc; a.z = z;
-        int rc = rows<T>(p, PRE_H, a, nb, s);
+        a.fac = static_cast<const cx<T>*>(p->hp_fac); a.fac_stride = p->n / 2 + 2;
+        int rc = rows<T>(p, use_plane ? PRE_HPLANE : PRE_H, a, nb, s);
         if (rc) return rc;
         // columns: inverse transform in place, optional |E|^2
         LineArgs<T> c = base_args<T>(p);

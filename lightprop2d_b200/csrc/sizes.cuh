@@ -29,6 +29,7 @@ struct Ops {
             case PRE_NONE: return launch_row<PRE_NONE>(a, s);
             case PRE_LENS: return launch_row<PRE_LENS>(a, s);
             case PRE_H:    return launch_row<PRE_H>(a, s);
+            case PRE_HPLANE: return launch_row<PRE_HPLANE>(a, s);
         }
         return cudaErrorInvalidValue;
     }
@@ -49,6 +50,7 @@ struct Ops {
         if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_NONE, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_NONE>::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_LENS, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_LENS>::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_H, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_H>::SMEM)) != cudaSuccess) return e;
+        if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_HPLANE, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_HPLANE>::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_NONE>, KC::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_H>, KC::SMEM)) != cudaSuccess) return e;
         return cudaSuccess;

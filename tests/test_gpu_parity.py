@@ -1170,3 +1170,30 @@ def test_two_step_column_pass_equals_one_kernel_pass(bits, n, monkeypatch):
     for x, y in zip(res["0"], res["1"]):
         assert rel_l2(y, x) <= tol
     assert not np.array_equal(res["0"][0], res["1"][0])          # (the two paths really are different kernels)
+
+
+@pytest.mark.parametrize("bits,n", [(128, 1024), (128, 2048), (64, 4096), (64, 128)])
+def test_h_plane_of_a_repeated_step(bits, n, monkeypatch):
+    """One-kernel-per-pass sizes: from the second consecutive propagate(dz) with the same dz on, the row pass reads H
+    from a plane built once (factor_plane_kernel) instead of evaluating it per sample; the same FP64 expressions, so
+    the fields agree with LP2D_HPLANE=0 to the last bits (the compiler may contract the complex multiply differently
+    around the two sources of H), also when dz changes in between."""
+    from lightprop2d_b200 import beam2d as _b
+    rng = np.random.default_rng(n)
+    f0 = (rng.standard_normal((2, n, n)) + 1j * rng.standard_normal((2, n, n))).astype(CT[bits])
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LP2D_HPLANE", mode)
+        _b._PLAN_CACHE.clear()
+        b = Beam2D(0.4 * n / 1024, n, 532e-7, init_field=f0.copy(), complex_bits=bits, use_gpu=True, numpy_output=False)
+        _ = b.spectrum
+        res = []
+        for dz in (0.02, 0.02, 0.02, 0.05, 0.02, 0.02, -0.02, -0.02):
+            b.propagate(dz)
+            res.append(b.field.clone())
+        out[mode] = res
+    _b._PLAN_CACHE.clear()
+    for k, (x, y) in enumerate(zip(out["0"], out["1"])):
+        err = float((x - y).abs().max() / x.abs().max())
+        assert err <= (4e-7 if bits == 64 else 1e-15), (k, err)
+    assert torch.equal(out["0"][0], out["1"][0])              # (the first step: the plane does not exist yet)
