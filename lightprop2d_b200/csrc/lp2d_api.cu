@@ -112,6 +112,7 @@ struct lp2d_plan {
     int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
     int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
     int use_tma;               // final column stage of two-stage fused steps through the TMA unit
+    bool fused_prop;           // the stateful propagate uses the fused step kernel (default: as bit 1 of fused_ops, but see plan_create)
     int fused_ops;             // which steps use the fused step kernel: 1 plain fft2, 2 steps that store state
                                // (propagate, lens, mask + fft2), 4 the fresh field -> field chain
     // fused step kernel (pipe2.cuh)
@@ -430,7 +431,13 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     if (dtype == LP2D_C64 && n == 1024) ops_default = 7;
     if (dtype == LP2D_C64 && n == 256) ops_default = 3;
     if ((dtype == LP2D_C64 && n == 512) || (dtype == LP2D_C128 && n == 256)) ops_default = 7;
+    // second half of round 2 (profiles/r3v_pipe_vs_perpass*.log): with whole-batch passes and the H plane of a repeated
+    // step the one-kernel-per-pass path beats the fused kernel at 2048 complex64 (propagate 37.3 vs 45.9 us per beam,
+    // lens 42.3 vs 45.9) and, for the stateful propagate only, at 512 complex128 (3.53 vs 3.97; lens 3.77 vs 3.50)
+    if (dtype == LP2D_C64 && n == 2048) ops_default = 0;
     env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : ops_default;
+    p->fused_prop = (p->fused_ops & 2) != 0 && !(dtype == LP2D_C128 && n == 512 && env == nullptr);
+    env = getenv("LP2D_FUSED_PROP"); if (env) p->fused_prop = atoi(env) != 0;
     // opt-in: correct, but 6 % slower than per-thread accesses in the one-tile-per-CTA form
     env = getenv("LP2D_TMA"); p->use_tma = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_PERSIST"); p->pipe_persist = env ? atoi(env) : 0;
@@ -458,7 +465,7 @@ int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
                      p->n, p->xl32 ? p->xl32->e : p->xl64->e, p->xl32 ? p->xl32->cl : p->xl64->cl);
         return 0;
     }
-    const bool fused = (p->p2_32 != nullptr || p->p2_64 != nullptr) && (p->fused_ops & 2);
+    const bool fused = (p->p2_32 != nullptr || p->p2_64 != nullptr) && p->fused_prop;
     if (name != nullptr && name_len > 0) {
         if (fused) {
             const bool q4 = (p->q4_32 != nullptr || p->q4_64 != nullptr) && (p->q4_ops & 2);
@@ -987,7 +994,7 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         // stage's transposed store lands the field in its natural orientation
         st[1].out_t = p->spectrum_t;
         st[1].moments = moments; st[1].dL = dL;                 // (zeroed by the caller; inverse stage only; the per-pass path ignores them)
-        const int rc = (p->spectrum_t || (p->fused_ops & 2)) ? run_p2<T>(p, st, 2, P2_FAC_H, p->spectrum_t, z, 0.0, batch, s, 2) : -1;
+        const int rc = (p->spectrum_t || p->fused_prop) ? run_p2<T>(p, st, 2, P2_FAC_H, p->spectrum_t, z, 0.0, batch, s, 2) : -1;
         if (rc >= 0) {
             if (moments_done != nullptr) *moments_done = (rc == 0 && moments != nullptr);
             return rc;

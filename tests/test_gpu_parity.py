@@ -752,12 +752,16 @@ def test_modes_project_tensor_core(n, nb, nmodes, batch):
 # ----------------------------------------------------------------------------- fused step kernel: every entry
 @pytest.mark.gpu
 @pytest.mark.parametrize("bits,n", [(64, 256), (64, 512), (64, 1024), (128, 256), (128, 512)])
-def test_fused_step_paths_batched(bits, n):
+def test_fused_step_paths_batched(bits, n, monkeypatch):
     """The sizes served by the fused step kernel (t3_kernel), batch of 3 beams, every step that stores
     state: propagate (+z, -z), lens, coordinate_filter (bool generator mask, complex array mask) and
-    spectral_filter (real array mask -> the inverse two-stage chain with a mask at load), against the oracle."""
+    spectral_filter (real array mask -> the inverse two-stage chain with a mask at load), against the oracle.
+    (LP2D_FUSED_PROP=1: also where the stateful propagate defaults to the one-kernel-per-pass path, 512 complex128.)"""
     import ctypes as C
     from lightprop2d_b200 import _lib as L
+    from lightprop2d_b200 import beam2d as _b
+    monkeypatch.setenv("LP2D_FUSED_PROP", "1")
+    _b._PLAN_CACHE.clear()
     rng = np.random.default_rng(n + bits)
     f0 = (rng.standard_normal((3, n, n)) + 1j * rng.standard_normal((3, n, n))).astype(CT[bits])
     area, wl = 4e-1 * n / 1024, 532e-7
