@@ -13,10 +13,12 @@ static const SizeOps<double> kOpsF64[] = {
     Ops<double, 1024, 16, 2, 4>::entry(),
     Ops<double, 1024, 8, 2, 4>::entry(1),
     Ops<double, 1024, 8, 2, 8>::entry(2),
-    Ops<double, 2048, 8, 1, 2>::entry(),
+    // E = 16 (two exchanges) with whole-batch passes: fft2 58.9 vs 65.7, stateful 73.2 vs 77.6, chain 113.7 vs 127.6 us per
+    // beam against the round-1 default E = 8 (profiles/r3w_variants_whole_batch.log)
+    Ops<double, 2048, 16, 1, 2>::entry(),
     Ops<double, 2048, 8, 1, 4>::entry(1),
     Ops<double, 2048, 16, 2, 4>::entry(2),
-    Ops<double, 2048, 16, 1, 2>::entry(3),
+    Ops<double, 2048, 8, 1, 2>::entry(3),
     Ops<double, 4096, 8, 1, 2>::entry(),
     Ops<double, 4096, 8, 1, 1>::entry(1),
 };
