@@ -140,6 +140,10 @@ struct lp2d_plan {
     double hp_z, hp_seen_z;    // z the plane holds / z of the previous stateful call
     bool hp_valid, hp_seen;
     int hp_mode;               // LP2D_HPLANE: 0 never, 1 automatic (default), 2 always
+    // the H plane and the column scratch are per-plan buffers: a call on another stream than the previous one that
+    // used them first waits for that stream (calls on one stream are ordered anyway)
+    cudaStream_t side_stream;
+    bool side_used;
     int spectrum_t;            // spectra of this plan are stored TRANSPOSED (lp2d_plan_set_spectrum_layout)
     int q4_colpriv;            // persistent form: warp-private final column stage (swizzled TMA tile + TMA store)
     int q4_ops;                // which steps use the persistent form (bits as fused_ops): measured per size, r2g_sweep*.log
@@ -284,6 +288,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     }
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
     p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr; p->spectrum_t = 0;
+    p->side_stream = nullptr; p->side_used = false;
     p->hp_fac = nullptr; p->hp_z = 0; p->hp_seen_z = 0; p->hp_valid = false; p->hp_seen = false;
     env = getenv("LP2D_HPLANE"); p->hp_mode = env ? atoi(env) : 1;
     p->cs_a = p->cs_b = 0; p->cs32[0] = p->cs32[1] = nullptr; p->cs64[0] = p->cs64[1] = nullptr;
@@ -798,7 +803,7 @@ long long chunk_beams(const lp2d_plan* p, long long batch) {
     // Planes of 16 MB and more (complex128 from 1024 points, complex64 from 2048): a chunk would be one or two beams,
     // i.e. launches of one or two waves fanned out over streams that then compete for L2; the whole batch per pass is
     // 13-24 % faster there (profiles/r3k_sweep_perpass_sizes.log: 4096^2 complex64 239 -> 181 us per beam)
-    if (c < 4 && !p->chunk_explicit) c = batch;
+    if ((c < 4 && !p->chunk_explicit) || p->cs_a != 0) c = batch;      // (the two-step column pass owns ONE scratch: one stream)
     if (c < 1) c = 1;
     // keep the row-count of a launch inside int range
     const long long cap = (long long)(0x7fffffff) / p->n;
@@ -846,6 +851,17 @@ int rows(const lp2d_plan* p, int pre, LineArgs<T> a, long long beams, cudaStream
     LP2D_CU(ops_of<T>(p)->row(pre, a, s), "row pass launch");
     return LP2D_OK;
 }
+static int claim_side_buffers(lp2d_plan* p, cudaStream_t s) {
+    if (p->side_used && p->side_stream != s) {
+        if (cudaStreamSynchronize(p->side_stream) != cudaSuccess) {
+            cudaGetLastError();                         // the previous stream no longer exists: wait for the device
+            LP2D_CU(cudaDeviceSynchronize(), "plan buffers: device synchronise");
+        }
+    }
+    p->side_stream = s; p->side_used = true;
+    return LP2D_OK;
+}
+
 template <typename T> const ColStepOps<T>* cs_of(const lp2d_plan* p, int i);
 template <> const ColStepOps<float>* cs_of<float>(const lp2d_plan* p, int i) { return p->cs32[i]; }
 template <> const ColStepOps<double>* cs_of<double>(const lp2d_plan* p, int i) { return p->cs64[i]; }
@@ -855,6 +871,7 @@ template <> const ColStepOps<double>* cs_of<double>(const lp2d_plan* p, int i) {
 template <typename T>
 int cols_two_step(lp2d_plan* p, const LineArgs<T>& a, long long beams, cudaStream_t s) {
     const long long n = p->n, plane = n * n;
+    { const int rc = claim_side_buffers(p, s); if (rc) return rc; }
     // One beam at a time through a scratch of one plane (default), or one PANEL of columns at a time
     // (LP2D_COLSTEP_PANEL_MB > 0): the scratch of a panel (n rows x wp columns) is then written by step 1 and read by
     // step 2 while it is still in L2, so the pass moves 2 P B through HBM like the one-kernel pass -- but in launches of
@@ -1009,6 +1026,7 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
     // pass 17-25 % of the whole step (profiles/r3s_h_cost.log).  Needs even tables (the fold).
     bool use_plane = false;
     if (p->hp_mode != 0 && p->h_even) {
+        { const int rc = claim_side_buffers(p, s); if (rc) return rc; }
         if (p->hp_valid && p->hp_z == z) use_plane = true;
         else if (p->hp_mode == 2 || (p->hp_seen && p->hp_seen_z == z)) {
             const int fl = p->n / 2 + 2;
