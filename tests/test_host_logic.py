@@ -88,3 +88,19 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
                 assert "numpy.fft.fft2" not in text and "np.fft.fft2" not in text and "np.fft.ifft2" not in text, f
+
+
+def test_device_profiles_mirror_the_host_generators_and_need_a_gpu():
+    """device_profiles has the reference's generator names with the same positional arguments (profiles.py:35-136) and,
+    like the rest of the product path, no CPU fallback."""
+    import inspect
+    from lightprop2d_b200 import device_profiles as dp
+    assert tuple(dp.__all__) == tuple(prof.__all__)
+    for name in prof.__all__:
+        host = [p.name for p in inspect.signature(getattr(prof, name)).parameters.values()]
+        dev = [p.name for p in inspect.signature(getattr(dp, name)).parameters.values() if p.kind != p.VAR_KEYWORD]
+        assert dev == host, (name, dev, host)
+    if not torch.cuda.is_available():
+        x = np.arange(-8, 8) * 1e-4
+        with pytest.raises(RuntimeError, match="CUDA"):
+            dp.round_hole(x, x.reshape(-1, 1), 5e-4)
