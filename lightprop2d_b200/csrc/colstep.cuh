@@ -105,7 +105,7 @@ struct ColStepOps {
     cudaError_t (*configure)(int* ctas_per_sm);
     void (*twiddles)(std::vector<double>& re_im);
 };
-const ColStepOps<float>* find_colstep_f32(int l);
-const ColStepOps<double>* find_colstep_f64(int l);
+const ColStepOps<float>* find_colstep_f32(int l, int variant);
+const ColStepOps<double>* find_colstep_f64(int l, int variant);
 
 }  // namespace lp2d

@@ -134,6 +134,7 @@ struct lp2d_plan {
     size_t cs_scratch_bytes;
     int cs_ctas[2];
     int cs_sms;
+    int cs_grid_mult;          // CTAs per launch = SMs x resident CTAs x this (0: one CTA per item)
     int cs_panel_mb;           // column panel whose scratch stays in L2 between the two steps (0: whole planes)
     // one-kernel-per-pass path: H plane of a repeated step (z-sweeps): built when a z comes a second time in a row
     void* hp_fac;              // [n][n/2 + 2], allocated on first use
@@ -380,9 +381,12 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             if (a > b) { const int t = a; a = b; b = t; }
             const int len[2] = {a, b};
             bool ok = true;
+            const char* ev = getenv("LP2D_COLSTEP_VARIANT");
+            const int csvar = ev ? atoi(ev) : 0;
+            ev = getenv("LP2D_COLSTEP_GRID"); p->cs_grid_mult = ev ? atoi(ev) : 4;
             for (int i = 0; i < 2 && ok; ++i) {
-                if (dtype == LP2D_C64) { p->cs32[i] = find_colstep_f32(len[i]); ok = p->cs32[i] != nullptr && p->cs32[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
-                else { p->cs64[i] = find_colstep_f64(len[i]); ok = p->cs64[i] != nullptr && p->cs64[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
+                if (dtype == LP2D_C64) { p->cs32[i] = find_colstep_f32(len[i], csvar); ok = p->cs32[i] != nullptr && p->cs32[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
+                else { p->cs64[i] = find_colstep_f64(len[i], csvar); ok = p->cs64[i] != nullptr && p->cs64[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
                 if (ok && p->cs_ctas[i] < 1) ok = false;
             }
             const size_t csz = dtype == LP2D_C64 ? sizeof(float2) : sizeof(double2);
@@ -919,7 +923,7 @@ int cols_two_step(lp2d_plan* p, const LineArgs<T>& a, long long beams, cudaStrea
                     c.stream_out = (a.flags & F_OUT_STREAM) ? 1 : 0;
                 }
                 c.nitems = (long long)c.U * c.tiles;
-                long long grid = (long long)p->cs_sms * p->cs_ctas[step] * 4;
+                long long grid = p->cs_grid_mult > 0 ? (long long)p->cs_sms * p->cs_ctas[step] * p->cs_grid_mult : c.nitems;
                 if (grid > c.nitems) grid = c.nitems;
                 LP2D_CU(ops->launch(c, (unsigned)grid, s), "two-step column pass launch");
             }

@@ -38,22 +38,47 @@ struct CSInst {
     static constexpr ColStepOps<T> entry() { return ColStepOps<T>{L, E, WC, K::LP::tw_size(), &launch, &configure, &twiddles}; }
 };
 
+// (variant 0 first; LP2D_COLSTEP_VARIANT picks another tile shape of the same line length)
 static const ColStepOps<float> kCS32[] = {
     CSInst<float, 32, 8, 32>::entry(),
     CSInst<float, 64, 8, 32>::entry(),
     CSInst<float, 128, 16, 32>::entry(),
+    CSInst<float, 32, 8, 64>::entry(),
+    CSInst<float, 64, 8, 64>::entry(),
+    CSInst<float, 128, 16, 64>::entry(),
+    CSInst<float, 32, 16, 32>::entry(),
+    CSInst<float, 64, 16, 32>::entry(),
+    CSInst<float, 128, 8, 32>::entry(),
 };
 static const ColStepOps<double> kCS64[] = {
     CSInst<double, 32, 8, 16>::entry(),
     CSInst<double, 64, 8, 16>::entry(),
     CSInst<double, 128, 16, 16>::entry(),
+    CSInst<double, 32, 8, 32>::entry(),
+    CSInst<double, 64, 8, 32>::entry(),
+    CSInst<double, 128, 16, 32>::entry(),
+    CSInst<double, 32, 16, 16>::entry(),
+    CSInst<double, 64, 16, 16>::entry(),
+    CSInst<double, 128, 8, 16>::entry(),
 };
-const ColStepOps<float>* find_colstep_f32(int l) {
-    for (const auto& o : kCS32) if (o.l == l) return &o;
-    return nullptr;
+const ColStepOps<float>* find_colstep_f32(int l, int variant) {
+    const ColStepOps<float>* first = nullptr;
+    int seen = 0;
+    for (const auto& o : kCS32) {
+        if (o.l != l) continue;
+        if (seen++ == variant) return &o;
+        if (first == nullptr) first = &o;
+    }
+    return first;
 }
-const ColStepOps<double>* find_colstep_f64(int l) {
-    for (const auto& o : kCS64) if (o.l == l) return &o;
-    return nullptr;
+const ColStepOps<double>* find_colstep_f64(int l, int variant) {
+    const ColStepOps<double>* first = nullptr;
+    int seen = 0;
+    for (const auto& o : kCS64) {
+        if (o.l != l) continue;
+        if (seen++ == variant) return &o;
+        if (first == nullptr) first = &o;
+    }
+    return first;
 }
 }  // namespace lp2d
