@@ -383,7 +383,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
             bool ok = true;
             const char* ev = getenv("LP2D_COLSTEP_VARIANT");
             const int csvar = ev ? atoi(ev) : 0;
-            ev = getenv("LP2D_COLSTEP_GRID"); p->cs_grid_mult = ev ? atoi(ev) : 4;
+            ev = getenv("LP2D_COLSTEP_GRID"); p->cs_grid_mult = ev ? atoi(ev) : 8;
             for (int i = 0; i < 2 && ok; ++i) {
                 if (dtype == LP2D_C64) { p->cs32[i] = find_colstep_f32(len[i], csvar); ok = p->cs32[i] != nullptr && p->cs32[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }
                 else { p->cs64[i] = find_colstep_f64(len[i], csvar); ok = p->cs64[i] != nullptr && p->cs64[i]->configure(&p->cs_ctas[i]) == cudaSuccess; }

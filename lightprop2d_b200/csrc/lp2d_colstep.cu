@@ -38,28 +38,17 @@ struct CSInst {
     static constexpr ColStepOps<T> entry() { return ColStepOps<T>{L, E, WC, K::LP::tw_size(), &launch, &configure, &twiddles}; }
 };
 
-// (variant 0 first; LP2D_COLSTEP_VARIANT picks another tile shape of the same line length)
+// (measured, profiles/r3y_colstep_variants.log: 512-byte tiles and E = 16 / 8 swapped are 3-20 % slower than these; the
+// two steps together stream 4 P B at 0.91 of the HBM peak at 4096^2 complex128)
 static const ColStepOps<float> kCS32[] = {
     CSInst<float, 32, 8, 32>::entry(),
     CSInst<float, 64, 8, 32>::entry(),
     CSInst<float, 128, 16, 32>::entry(),
-    CSInst<float, 32, 8, 64>::entry(),
-    CSInst<float, 64, 8, 64>::entry(),
-    CSInst<float, 128, 16, 64>::entry(),
-    CSInst<float, 32, 16, 32>::entry(),
-    CSInst<float, 64, 16, 32>::entry(),
-    CSInst<float, 128, 8, 32>::entry(),
 };
 static const ColStepOps<double> kCS64[] = {
     CSInst<double, 32, 8, 16>::entry(),
     CSInst<double, 64, 8, 16>::entry(),
     CSInst<double, 128, 16, 16>::entry(),
-    CSInst<double, 32, 8, 32>::entry(),
-    CSInst<double, 64, 8, 32>::entry(),
-    CSInst<double, 128, 16, 32>::entry(),
-    CSInst<double, 32, 16, 16>::entry(),
-    CSInst<double, 64, 16, 16>::entry(),
-    CSInst<double, 128, 8, 16>::entry(),
 };
 const ColStepOps<float>* find_colstep_f32(int l, int variant) {
     const ColStepOps<float>* first = nullptr;
