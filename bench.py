@@ -531,6 +531,65 @@ def run_ours(args):
     except Exception as e:                                    # noqa: BLE001  (reported, never hidden)
         c128 = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- the other BASELINE configs, device-side, one GPU (rank 0 of a one-GPU run): config 2 (single complex128 field
+    # z-sweep step), config 3 (512^2 complex64 ensemble: fft2 -> H -> ifft2 -> |E|^2 per beam), config 5 (mode projection)
+    configs = None
+    if world == 1:
+        configs = {}
+
+        def ev_ms(fn, iters, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a_, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(iters):
+                fn()
+            b2.record()
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b2) / iters
+
+        try:
+            for nn in (1024, 2048, 4096):
+                bm = lp.Beam2D(AREA, nn, WL, init_field_gen=lp.gaussian_beam, init_gen_args=(1, 0.05), complex_bits=128,
+                               use_gpu=True, numpy_output=False, device=local_rank)
+                bm.lens(10.0)
+                t_ms = ev_ms(lambda: bm.propagate(DZ), 20)
+                configs[f"config2_single_field_c128_{nn}"] = {
+                    "us_per_propagate": t_ms * 1e3, "roofline_frac": 3 * nn * nn * 16 / (t_ms * 1e-3) / 1e9 / peak,
+                    "kernel": ctypes_name(lib, bm._plan.handle)}
+                del bm
+            torch.cuda.empty_cache()
+            nb3 = 1024
+            prop3 = EnsemblePropagator(200e-4 * 2, 512, 632e-7, complex_bits=64, device=local_rank)
+            f3 = prop3.random_fields(nb3, 150e-4, seed=11, phase=True)
+            out3 = torch.empty(nb3, 512, 512, dtype=torch.float32, device=dev)
+            t_ms = ev_ms(lambda: prop3.intensity(f3, 100e-4, out=out3), 10)
+            configs["config3_ensemble_c64_512"] = {
+                "beams_per_s": nb3 / (t_ms * 1e-3), "us_per_beam": t_ms * 1e3 / nb3,
+                "roofline_frac": nb3 * 512 * 512 * 12 / (t_ms * 1e-3) / 1e9 / peak,
+                "work": "device-generated random_round_hole_phase fields -> fft2 -> H -> ifft2 -> |E|^2, one fused launch per batch"}
+            del prop3, f3, out3
+            torch.cuda.empty_cache()
+            for bits5, bt in ((64, 64), (128, 16)):
+                ct5 = torch.complex64 if bits5 == 64 else torch.complex128
+                modes = torch.randn(256, 512 * 512, dtype=ct5, device=dev)
+                fld5 = torch.randn(bt, 512, 512, dtype=ct5, device=dev)
+                b5 = lp.Beam2D(200e-4 * 2, 512, 632e-7, init_field=fld5, complex_bits=bits5, use_gpu=True, numpy_output=False,
+                               device=local_rank)
+                c5 = b5.deconstruct_by_modes(modes)
+                t_p = ev_ms(lambda: b5.deconstruct_by_modes(modes), 5, 2)
+                t_s = ev_ms(lambda: b5.construct_by_modes(modes, c5), 5, 2)
+                byt = (256 * 512 * 512 + bt * 512 * 512) * (8 if bits5 == 64 else 16)
+                configs[f"config5_modes_c{bits5}_256x512x512_{bt}beams"] = {
+                    "project_ms": t_p, "synthesize_ms": t_s, "project_algorithmic_gbs": byt / (t_p * 1e-3) / 1e9,
+                    "project_tflops": 8.0 * bt * 256 * 512 * 512 / (t_p * 1e-3) / 1e12,
+                    "kernel": "tcgen05 3xTF32 (complex64)" if bits5 == 64 else "register-tiled FP64 GEMM, split k (complex128)"}
+                del b5, modes, fld5, c5
+            torch.cuda.empty_cache()
+        except Exception as e:                                # noqa: BLE001  (reported, never hidden)
+            configs["error"] = f"{type(e).__name__}: {e}"
+
     # ---- one grid over all the ranks (BASELINE config 4): slab decomposition + all-to-all exchange, N >= 2
     slab = None
     if world > 1:
@@ -559,7 +618,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "npoints": n, "complex_bits": BITS, "beams_per_gpu": B,
                        "total_beams": total_beams, "sharding": "contiguous beam blocks, no collective",
                        "l2": "inputs (2 GiB spectrum + 2 GiB field per GPU) are larger than the 126 MB L2; no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "configs": configs,
             "c128": c128, "secondary_baselines": sec,
         }
         if slab is not None:

@@ -485,7 +485,11 @@ int lp2d_plan_step_kernel(lp2d_plan* p, char* name, int name_len) {
                      q4 ? ", persistent: TMA / bulk-copy producer + transform warps" : "");
         } else {
             const int e = p->ops32 ? p->ops32->e : p->ops64->e;
-            snprintf(name, (size_t)name_len, "line_kernel<%s, N=%d, E=%d> row pass + column pass", p->dtype == LP2D_C64 ? "float" : "double", p->n, e);
+            if (p->cs_a != 0)
+                snprintf(name, (size_t)name_len, "line_kernel<%s, N=%d, E=%d> row pass + colstep_kernel x 2 (columns as %d x %d)",
+                         p->dtype == LP2D_C64 ? "float" : "double", p->n, e, p->cs_a, p->cs_b);
+            else
+                snprintf(name, (size_t)name_len, "line_kernel<%s, N=%d, E=%d> row pass + column pass", p->dtype == LP2D_C64 ? "float" : "double", p->n, e);
         }
     }
     return fused ? 1 : 0;
