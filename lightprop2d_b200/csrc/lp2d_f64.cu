@@ -10,9 +10,12 @@ static const SizeOps<double> kOpsF64[] = {
     Ops<double, 256, 8, 8, 8>::entry(),
     Ops<double, 512, 8, 4, 4>::entry(),
     // 1024: E = 16 (two exchanges instead of three): fresh chain +16 %, stateful +3 % (profiles/r1c_large_n_variants.log)
-    Ops<double, 1024, 16, 2, 4>::entry(),
+    // (one row per CTA with whole-batch passes: 15.62 vs 15.91 us per beam stateful, 12.81 vs 13.09 fft2; 128-byte column
+    // tiles (W = 8, one 512-thread CTA per SM): 17.5)
+    Ops<double, 1024, 16, 1, 4>::entry(),
     Ops<double, 1024, 8, 2, 4>::entry(1),
     Ops<double, 1024, 8, 2, 8>::entry(2),
+    Ops<double, 1024, 16, 2, 4>::entry(3),
     // E = 16 (two exchanges) with whole-batch passes: fft2 58.9 vs 65.7, stateful 73.2 vs 77.6, chain 113.7 vs 127.6 us per
     // beam against the round-1 default E = 8 (profiles/r3w_variants_whole_batch.log)
     Ops<double, 2048, 16, 1, 2>::entry(),
