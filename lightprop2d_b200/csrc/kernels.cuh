@@ -27,7 +27,7 @@ enum { AX_ROW = 0, AX_COL = 1 };
 // the kx -> -kx symmetry) instead of being evaluated in FP64 per sample: a z-sweep with a constant step, single field,
 // spends a quarter of its row pass on sqrt / sincospi otherwise (profiles/r3s_h_cost.log)
 enum { PRE_NONE = 0, PRE_LENS = 1, PRE_H = 2, PRE_HPLANE = 3 };
-enum { MID_NONE = 0, MID_H = 1 };
+enum { MID_NONE = 0, MID_H = 1, MID_HPLANE = 2 };     // MID_HPLANE: as MID_H with H read from the plane of PRE_HPLANE
 enum { F_INVERSE = 1,
        F_IN_STREAM = 2,     // input is read once: evict-first loads
        F_OUT_STREAM = 4,    // output is not re-read soon: evict-first stores
@@ -267,14 +267,21 @@ line_kernel(const LineArgs<T> p) {
             for (int m = 0; m < E; ++m) st_cx(&p.out_pre[gb + (t + TPL * m) * STRIDE], v[m], state_stream);
         }
 
-        if constexpr (MID == MID_H) {
+        if constexpr (MID == MID_H || MID == MID_HPLANE) {
             // column pass of the fresh chain: FFT_y, transfer function, inverse FFT_y
             line_fft<T, N, E, K::SYNC>(v, sline, p.tw, t, l);
-            const double a_i = __ldg(&p.a_tab[fixed]);            // AXIS == AX_COL
+            if constexpr (MID == MID_H) {
+                const double a_i = __ldg(&p.a_tab[fixed]);        // AXIS == AX_COL
 #pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const cx<T> h = transfer_factor<T>(a_i, __ldg(&p.b_tab[t + TPL * m]), p.z);
-                v[m] = cmul(v[m], h);
+                for (int m = 0; m < E; ++m) {
+                    const cx<T> h = transfer_factor<T>(a_i, __ldg(&p.b_tab[t + TPL * m]), p.z);
+                    v[m] = cmul(v[m], h);
+                }
+            } else {
+                // plane [row j][min(i, N - i)]: the W threads of a grid row read W consecutive (or mirrored) entries
+                const int fi = fixed <= N / 2 ? fixed : N - fixed;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = cmul(v[m], __ldg(p.fac + (long long)(t + TPL * m) * p.fac_stride + fi));
             }
             if (p.out_mid != nullptr && active) {
 #pragma unroll

@@ -140,6 +140,9 @@ struct lp2d_plan {
     void* hp_fac;              // [n][n/2 + 2], allocated on first use
     double hp_z, hp_seen_z;    // z the plane holds / z of the previous stateful call
     bool hp_valid, hp_seen;
+    cudaStream_t hp_stream;    // stream the plane was built on; hp_event: the build; hp_multi: other streams have read it
+    cudaEvent_t hp_event;
+    bool hp_multi;
     int hp_mode;               // LP2D_HPLANE: 0 never, 1 automatic (default), 2 always
     // the H plane and the column scratch are per-plan buffers: a call on another stream than the previous one that
     // used them first waits for that stream (calls on one stream are ordered anyway)
@@ -290,6 +293,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     p->counter_set = 0; p->counters_used[0] = p->counters_used[1] = 0;
     p->q4_32 = nullptr; p->q4_64 = nullptr; p->q4_ctas = 0; p->q4_lag = 0; p->q4_ops = 0; p->q4_colpriv = 0; p->q4_timing = nullptr; p->spectrum_t = 0;
     p->side_stream = nullptr; p->side_used = false;
+    p->hp_stream = nullptr; p->hp_event = nullptr; p->hp_multi = false;
     p->hp_fac = nullptr; p->hp_z = 0; p->hp_seen_z = 0; p->hp_valid = false; p->hp_seen = false;
     env = getenv("LP2D_HPLANE"); p->hp_mode = env ? atoi(env) : 1;
     p->cs_a = p->cs_b = 0; p->cs32[0] = p->cs32[1] = nullptr; p->cs64[0] = p->cs64[1] = nullptr;
@@ -519,6 +523,7 @@ int lp2d_plan_destroy(lp2d_plan* p) {
     if (p == nullptr) return LP2D_OK;
     cudaFree(p->q4_timing);
     cudaFree(p->hp_fac);
+    if (p->hp_event) cudaEventDestroy(p->hp_event);
     cudaFree(p->cs_tw[0]); cudaFree(p->cs_tw[1]); cudaFree(p->cs_tw4); cudaFree(p->cs_scratch);
     cudaFree(p->tw);
     cudaFree(p->tabs);
@@ -948,6 +953,44 @@ int cols(const lp2d_plan* p, int mid, LineArgs<T> a, long long beams, cudaStream
     return LP2D_OK;
 }
 
+// The H plane of a repeated step on the one-kernel-per-pass path: the second consecutive call with the same z builds it
+// (FP64, reference operation order, half the samples by the kx fold), later calls read it.  *use = the plane holds H(z).
+template <typename T>
+int ensure_h_plane(lp2d_plan* p, double z, cudaStream_t s, bool* use) {
+    *use = false;
+    if (p->hp_mode == 0 || !p->h_even) return LP2D_OK;
+    if (p->hp_valid && p->hp_z == z) {
+        // readers on other streams than the one that built the plane wait for the build (device-side), nothing else
+        if (s != p->hp_stream) {
+            LP2D_CU(cudaStreamWaitEvent(s, p->hp_event, 0), "H plane: wait for the build");
+            p->hp_multi = true;
+        }
+        *use = true;
+    } else if (p->hp_mode == 2 || (p->hp_seen && p->hp_seen_z == z)) {
+        const int fl = p->n / 2 + 2;
+        if (p->hp_fac == nullptr) {
+            if (cudaMalloc(&p->hp_fac, (size_t)p->n * fl * sizeof(cx<T>)) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->hp_event, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError(); cudaFree(p->hp_fac); p->hp_fac = nullptr;
+            }
+        } else if (p->hp_valid) {
+            // rebuilt for another z: everything that still reads the old plane must be done
+            if (p->hp_multi) { LP2D_CU(cudaDeviceSynchronize(), "H plane: device synchronise"); }
+            else if (s != p->hp_stream && cudaStreamSynchronize(p->hp_stream) != cudaSuccess) { cudaGetLastError(); LP2D_CU(cudaDeviceSynchronize(), "H plane: device synchronise"); }
+        }
+        if (p->hp_fac != nullptr) {
+            cudaError_t e = sizeof(T) == 4
+                ? p2_factor_plane_f32(static_cast<float2*>(p->hp_fac), p->tabs, p->n, fl, P2_FAC_H, 0, 0, z, 0.0, 0.0, s)
+                : p2_factor_plane_f64(static_cast<double2*>(p->hp_fac), p->tabs, p->n, fl, P2_FAC_H, 0, 0, z, 0.0, 0.0, s);
+            if (e != cudaSuccess) return cuda_fail(e, "H plane launch");
+            LP2D_CU(cudaEventRecord(p->hp_event, s), "H plane: event");
+            p->hp_valid = true; p->hp_z = z; p->hp_stream = s; p->hp_multi = false; *use = true;
+        }
+    }
+    p->hp_seen = true; p->hp_seen_z = z;
+    return LP2D_OK;
+}
+
 // data *= mask (optional), state stored to `data`, other = (i)fft2(data)
 template <typename T>
 int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const void* mask, int mask_kind,
@@ -1033,22 +1076,7 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
     // order, half the samples by the kx fold), later calls read it -- the per-sample evaluation costs a single-field row
     // pass 17-25 % of the whole step (profiles/r3s_h_cost.log).  Needs even tables (the fold).
     bool use_plane = false;
-    if (p->hp_mode != 0 && p->h_even) {
-        { const int rc = claim_side_buffers(p, s); if (rc) return rc; }
-        if (p->hp_valid && p->hp_z == z) use_plane = true;
-        else if (p->hp_mode == 2 || (p->hp_seen && p->hp_seen_z == z)) {
-            const int fl = p->n / 2 + 2;
-            if (p->hp_fac == nullptr && cudaMalloc(&p->hp_fac, (size_t)p->n * fl * sizeof(cx<T>)) != cudaSuccess) { cudaGetLastError(); p->hp_fac = nullptr; }
-            if (p->hp_fac != nullptr) {
-                cudaError_t e = sizeof(T) == 4
-                    ? p2_factor_plane_f32(static_cast<float2*>(p->hp_fac), p->tabs, p->n, fl, P2_FAC_H, 0, 0, z, 0.0, 0.0, s)
-                    : p2_factor_plane_f64(static_cast<double2*>(p->hp_fac), p->tabs, p->n, fl, P2_FAC_H, 0, 0, z, 0.0, 0.0, s);
-                if (e != cudaSuccess) return cuda_fail(e, "H plane launch");
-                p->hp_valid = true; p->hp_z = z; use_plane = true;
-            }
-        }
-        p->hp_seen = true; p->hp_seen_z = z;
-    }
+    { const int rc = ensure_h_plane<T>(p, z, s, &use_plane); if (rc) return rc; }
     Fan fan(p, s, (batch + cb - 1) / cb);
     LP2D_CU(fan.fork(), "stream fork");
     for (long long b0 = 0; b0 < batch; b0 += cb) {
@@ -1109,6 +1137,12 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
     }
     const T sc = (T)(1.0 / (double)p->n);
     const int H = p->hints;
+    // H plane of a repeated z for the fused column stage: complex64 only (2048^2: 59.2 -> 56.9 us per beam); the complex128
+    // column kernel is bound by its L1 wavefronts (67 % busy) and the plane reads cost more than the FP64 evaluation
+    // that otherwise runs in an idle pipe (1024^2: 24.2 -> 28.3)
+    bool use_plane = false;
+    if (sizeof(T) == 4) { const int rc = ensure_h_plane<T>(p, z, s, &use_plane); if (rc) return rc; }
+    else { p->hp_seen = true; p->hp_seen_z = z; }
     // the shared work buffer serialises the chunks; with per-chunk output buffers they fan out
     Fan fan(p, s, via_work ? 1 : (batch + cb - 1) / cb);
     LP2D_CU(fan.fork(), "stream fork");
@@ -1128,7 +1162,8 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
         c.in = buf; c.out = buf; c.z = z; c.scale = sc;
         c.flags = H ? F_STATE_STREAM : 0;
         c.out_mid = spec_out ? static_cast<cx<T>*>(spec_out) + b0 * plane : nullptr;
-        rc = cols<T>(p, MID_H, c, nb, s);
+        c.fac = static_cast<const cx<T>*>(p->hp_fac); c.fac_stride = p->n / 2 + 2;
+        rc = cols<T>(p, use_plane ? MID_HPLANE : MID_H, c, nb, s);
         if (rc) return rc;
         // 3. inverse row transform (scaled 1/N): buf -> field_out and/or |E|^2
         LineArgs<T> r = base_args<T>(p);

@@ -37,6 +37,7 @@ struct Ops {
         switch (mid) {
             case MID_NONE: return launch_col<MID_NONE>(a, s);
             case MID_H:    return launch_col<MID_H>(a, s);
+            case MID_HPLANE: return launch_col<MID_HPLANE>(a, s);
         }
         return cudaErrorInvalidValue;
     }
@@ -53,6 +54,7 @@ struct Ops {
         if ((e = optin(line_kernel<T, N, E, AX_ROW, WR, PRE_HPLANE, MID_NONE>, KCfg<T, N, E, AX_ROW, WR, PRE_HPLANE>::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_NONE>, KC::SMEM)) != cudaSuccess) return e;
         if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_H>, KC::SMEM)) != cudaSuccess) return e;
+        if ((e = optin(line_kernel<T, N, E, AX_COL, WC, PRE_NONE, MID_HPLANE>, KC::SMEM)) != cudaSuccess) return e;
         return cudaSuccess;
     }
     // exp(-2 pi i k r / (Ns R)) for every pass after the first, FP64 (rounded to T by the plan)

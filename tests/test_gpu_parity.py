@@ -1201,3 +1201,31 @@ def test_h_plane_of_a_repeated_step(bits, n, monkeypatch):
         err = float((x - y).abs().max() / x.abs().max())
         assert err <= (4e-7 if bits == 64 else 1e-15), (k, err)
     assert torch.equal(out["0"][0], out["1"][0])              # (the first step: the plane does not exist yet)
+
+
+@pytest.mark.parametrize("bits,n", [(128, 1024), (64, 2048), (64, 128)])
+def test_h_plane_in_the_fresh_chain_and_across_streams(bits, n, monkeypatch):
+    """The fused column stage of the one-kernel-per-pass chain (FFT, H, inverse FFT) reads the same H plane once a z
+    repeats; EnsemblePropagator runs its chunks on several streams that then share the plane.  Against LP2D_HPLANE=0."""
+    from lightprop2d_b200 import beam2d as _b
+    rng = np.random.default_rng(n + 1)
+    nb = 6
+    f0 = (rng.standard_normal((nb, n, n)) + 1j * rng.standard_normal((nb, n, n))).astype(CT[bits])
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("LP2D_HPLANE", mode)
+        _b._PLAN_CACHE.clear()
+        prop = EnsemblePropagator(0.4 * n / 1024, n, 532e-7, complex_bits=bits)
+        fd = torch.from_numpy(f0).cuda()
+        res = [prop.intensity(fd, z).clone() for z in (0.03, 0.03, 0.03, -0.01, 0.03, 0.03)]
+        if n <= 1024:
+            host_in = torch.from_numpy(f0).pin_memory()
+            for _ in range(3):
+                r = prop.intensity_from_host(host_in, 0.03, chunk=2)
+                torch.cuda.synchronize()
+                res.append(r.clone().cuda())
+        out[mode] = res
+    _b._PLAN_CACHE.clear()
+    for k, (x, y) in enumerate(zip(out["0"], out["1"])):
+        err = float((x - y).abs().max() / x.abs().max())
+        assert err <= (2e-6 if bits == 64 else 1e-14), (k, err)
