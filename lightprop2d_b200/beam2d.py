@@ -241,6 +241,9 @@ class Beam2D:
 
     def _call(self, name, *args):
         torch = _torch()
+        if torch.cuda.current_device() == self._tdev.index:       # (the device switch costs a few microseconds per call)
+            _lib.check(getattr(self._lib, name)(*args), name)
+            return
         with torch.cuda.device(self._tdev):
             _lib.check(getattr(self._lib, name)(*args), name)
 
