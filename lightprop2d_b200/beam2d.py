@@ -41,6 +41,8 @@ cm = 1
 m = 100
 
 _PLAN_CACHE: dict = {}
+# numpy dtypes that are uploaded as they are and cast to the complex type on the device
+_DEVICE_CAST = ("bool", "uint8", "int8", "int16", "int32", "int64", "float32", "float64")
 
 
 def _torch():
@@ -212,7 +214,9 @@ class Beam2D:
         if isinstance(data, torch.Tensor):
             t = data.to(self._tdev)
         elif isinstance(data, np.ndarray):
-            if np_complex is not None and data.dtype != np_complex:
+            # (a bool / real array is uploaded as it is and cast on the device -- same rounding as ``astype``, but not
+            # a complex copy 16x the size of an 8192^2 mask built on the host first)
+            if np_complex is not None and data.dtype != np_complex and data.dtype.name not in _DEVICE_CAST:
                 data = data.astype(np_complex)
             t = torch.from_numpy(np.ascontiguousarray(data)).to(self._tdev)
         else:
