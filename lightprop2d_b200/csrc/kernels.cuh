@@ -130,7 +130,9 @@ struct KCfg {
     static constexpr size_t SMEM_X = (LP::npass() > 1) ? (size_t)W * LS * sizeof(cx<T>) : 0;   // exchange
     // PRE_H keeps the transfer function of the CTA's W lines in shared memory so that it is
     // computed once and reused for every beam group the CTA walks over
-    static constexpr size_t SMEM_H = (PRE == PRE_H) ? (size_t)W * N * sizeof(cx<T>) : 0;
+    // (8192 complex128 points: exchange + H would not fit 227 KB; H is then evaluated where it is used, for every beam)
+    static constexpr bool H_IN_SMEM = (PRE == PRE_H) && (SMEM_X + (size_t)W * N * sizeof(cx<T>) <= 226 * 1024);
+    static constexpr size_t SMEM_H = H_IN_SMEM ? (size_t)W * N * sizeof(cx<T>) : 0;
     static constexpr size_t SMEM = SMEM_X + SMEM_H;
     // resident CTAs per SM the register allocation should allow: data registers are
     // 2*E*sizeof(T)/4, the butterflies need about as many again
@@ -188,7 +190,7 @@ line_kernel(const LineArgs<T> p) {
     const bool inv = (p.flags & F_INVERSE) != 0;
 
     cx<T>* sH = nullptr;
-    if constexpr (PRE == PRE_H) {
+    if constexpr (PRE == PRE_H && K::H_IN_SMEM) {
         // H for this thread's samples, kept at [line][pos]: written and read by the same thread
         sH = reinterpret_cast<cx<T>*>(smem_raw + K::SMEM_X) + l * N;
         const double fx = (AXIS == AX_ROW) ? __ldg(&p.b_tab[fixed]) : __ldg(&p.a_tab[fixed]);
@@ -250,9 +252,19 @@ line_kernel(const LineArgs<T> p) {
                 v[m] = cmul(v[m], lens_factor<T>(AXIS == AX_ROW ? g2 : f2, AXIS == AX_ROW ? f2 : g2, p.lens_k0, p.lens_2f));
             }
         }
-        if constexpr (PRE == PRE_H) {
+        if constexpr (PRE == PRE_H && K::H_IN_SMEM) {
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = cmul(v[m], sH[t + TPL * m]);
+        }
+        if constexpr (PRE == PRE_H && !K::H_IN_SMEM) {
+            const double fx = (AXIS == AX_ROW) ? __ldg(&p.b_tab[fixed]) : __ldg(&p.a_tab[fixed]);
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int pos = t + TPL * m;
+                const double a_i = (AXIS == AX_ROW) ? __ldg(&p.a_tab[pos]) : fx;
+                const double b_j = (AXIS == AX_ROW) ? fx : __ldg(&p.b_tab[pos]);
+                v[m] = cmul(v[m], transfer_factor<T>(a_i, b_j, p.z));
+            }
         }
         if constexpr (PRE == PRE_HPLANE && AXIS == AX_ROW) {
             const cx<T>* frow = p.fac + (long long)fixed * p.fac_stride;

@@ -182,7 +182,7 @@ int lp2d_version(void) { return LP2D_VERSION; }
 const char* lp2d_last_error(void) { return t_err.c_str(); }
 long long lp2d_launch_count(void) { return g_launches; }
 int lp2d_min_npoints(void) { return 16; }
-int lp2d_max_npoints(int dtype) { return dtype == LP2D_C64 ? 8192 : 4096; }
+int lp2d_max_npoints(int dtype) { (void)dtype; return 8192; }
 int lp2d_max_line_points(int dtype) { (void)dtype; return 32768; }
 
 int lp2d_grid_tables(int n, double area_size, double wl, double* X, double* Kx, double* a,
@@ -1109,6 +1109,14 @@ int propagate_fresh(lp2d_plan* p, const void* fin, void* fout, void* spec_out, v
     if (p->spectrum_t && spec_out != nullptr) {
         // transposed spectrum wanted as a by-product: fft2 (-> transposed spectrum), then the stateful step
         if (fout == nullptr) return fail(LP2D_EUNSUPPORTED, "propagate_field: transposed spectrum_out needs field_out");
+        int rc = mul_fft2<T>(p, fin, nullptr, spec_out, nullptr, 0, 0, batch, 0, PRE_NONE, 0, 0, s);
+        if (rc) return rc;
+        return propagate_state<T>(p, spec_out, fout, intensity, batch, z, s);
+    }
+    if (p->cs_a != 0 && spec_out != nullptr && fout != nullptr) {
+        // grids whose column pass runs in two steps: the fused column stage (FFT, H, inverse FFT) would need the
+        // one-kernel column pass with its 16-32-byte pieces (8192^2 complex128: 42 ms); with the spectrum wanted
+        // anyway, fft2 + the stateful step are four streaming passes instead
         int rc = mul_fft2<T>(p, fin, nullptr, spec_out, nullptr, 0, 0, batch, 0, PRE_NONE, 0, 0, s);
         if (rc) return rc;
         return propagate_state<T>(p, spec_out, fout, intensity, batch, z, s);

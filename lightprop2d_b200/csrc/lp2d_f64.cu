@@ -24,6 +24,10 @@ static const SizeOps<double> kOpsF64[] = {
     Ops<double, 2048, 8, 1, 2>::entry(3),
     Ops<double, 4096, 8, 1, 2>::entry(),
     Ops<double, 4096, 8, 1, 1>::entry(1),
+    // 8192 points (tests/gaussbeam_performance.py:15 runs it): a row is 128 KB, one CTA of 512 threads holds it (E = 16,
+    // three exchanges through 135 KB of shared memory); the column pass runs in two steps (colstep.cuh, 64 x 128), the
+    // one-column-per-CTA kernel below only serves the fused column stage of the fresh chain
+    Ops<double, 8192, 16, 1, 1>::entry(),
 };
 const SizeOps<double>* find_ops_f64(int n, int variant) {
     const SizeOps<double>* first = nullptr;
