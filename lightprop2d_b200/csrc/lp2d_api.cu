@@ -112,6 +112,7 @@ struct lp2d_plan {
     int pipe_hints;            // P2_HINT_* (L2 eviction priorities)
     int pipe_persist;          // launch the fused step kernel with an L2 persisting window over the ring
     int use_tma;               // final column stage of two-stage fused steps through the TMA unit
+    int fused_min_pct;         // ticket form only for launches of at least this many percent of the resident CTA slots per stage
     bool fused_prop;           // the stateful propagate uses the fused step kernel (default: as bit 1 of fused_ops, but see plan_create)
     int fused_ops;             // which steps use the fused step kernel: 1 plain fft2, 2 steps that store state
                                // (propagate, lens, mask + fft2), 4 the fresh field -> field chain
@@ -451,6 +452,7 @@ int lp2d_plan_create(lp2d_plan** out, int n, int dtype, const double* host_a, co
     env = getenv("LP2D_FUSED_OPS"); p->fused_ops = env ? atoi(env) : ops_default;
     p->fused_prop = (p->fused_ops & 2) != 0 && !(dtype == LP2D_C128 && n == 512 && env == nullptr);
     env = getenv("LP2D_FUSED_PROP"); if (env) p->fused_prop = atoi(env) != 0;
+    env = getenv("LP2D_FUSED_MIN"); p->fused_min_pct = env ? atoi(env) : 75;
     // opt-in: correct, but 6 % slower than per-thread accesses in the one-tile-per-CTA form
     env = getenv("LP2D_TMA"); p->use_tma = env ? atoi(env) : 0;
     env = getenv("LP2D_PIPE_PERSIST"); p->pipe_persist = env ? atoi(env) : 0;
@@ -610,7 +612,7 @@ int run_q4(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
            long long batch, cudaStream_t s) {
     const Q4Ops<T>* ops = q4_of<T>(p);
     if (ops == nullptr) return -1;
-    if (stages[nstages - 1].moments != nullptr) return -1;      // the fused moment sums live in the ticket form
+    if (stages[nstages - 1].moments != nullptr || stages[nstages - 1].probe_out != nullptr) return -1;   // fused sweep by-products: ticket form
     // bulk copies of the user rows need 16-byte aligned planes
     if (!stages[0].in_ring && (reinterpret_cast<uintptr_t>(stages[0].in) & 15) != 0) return -1;
     const long long plane = (long long)p->n * p->n * (long long)sizeof(cx<T>);
@@ -708,6 +710,14 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
     // fits L2), one for 1024 points (the ring would double to 64 MB)
     long long G = p->pipe_g > 0 ? p->pipe_g : (p->n <= 512 ? 2 : 1);
     if (G > batch) G = batch;
+    // Launches that do not fill the GPU (a single field, a handful of small beams): the dependent stages of the fused
+    // kernel are then a serial chain of CTA lifetimes, and two plain launches are faster (1024^2 single field 17.5 vs
+    // 20.6 us, 512^2 x 4 beams 4.0 vs 6.5 us per beam; from 1024^2 x 2 / 512^2 x 16 on the fused kernel wins again:
+    // profiles/r3z_small_batches.log).  Threshold: items per stage against 3/4 of the resident CTA slots
+    // (LP2D_FUSED_MIN: percent of the slots, default 75; 0: always fused).  The transposed layout exists only here.
+    if (!p->spectrum_t && p->fused_min_pct > 0 &&
+        ((batch + G - 1) / G) * (long long)tiles * 100 < conc * (long long)p->fused_min_pct)
+        return -1;
     // lag (in groups) between consecutive stages of a group: the items in between cover every resident
     // CTA (with a margin), so that what an item depends on was drawn more than a wave earlier
     const long long reach = (5 * conc) / 4;
@@ -750,6 +760,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
             if (st.out_mid) st.out_mid += off;
             if (st.inten) st.inten += off;
             if (st.moments) st.moments += b0 * 5;
+            if (st.probe_out) st.probe_out += b0;
             if (st.mask) st.mask = static_cast<const char*>(st.mask) + b0 * st.mask_beam_stride *
                                    (st.mask_kind == MASK_CX ? sizeof(cx<T>) : st.mask_kind == MASK_REAL ? sizeof(T) : 1);
         }
@@ -767,7 +778,7 @@ int run_p2(lp2d_plan* p, const P2Stage<T>* stages, int nstages, int fac_kind, in
         a.fac_stride = (fac_kind == P2_FAC_LENS && !p->x2_even) ? p->n : ops->fl;
         a.hints = p->pipe_hints >= 0 ? p->pipe_hints : (P2_HINT_KEEP_RING | 1 | (nstages == 2 ? P2_HINT_PREFETCH : 0));
         a.use_tma = 0;
-        if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && !a.st[1].out_t && a.st[1].moments == nullptr && a.st[1].out != nullptr &&
+        if (p->use_tma && nstages == 2 && a.st[1].in_ring && !a.st[1].mid && !a.st[1].out_t && a.st[1].moments == nullptr && a.st[1].probe_out == nullptr && a.st[1].out != nullptr &&
             (ops->w * (int)sizeof(cx<T>)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.st[1].out) & 15) == 0) {
             const int box_rows = p->n < 256 ? p->n : 256;
             if (encode_plane_map(&a.tm_ring, p->ring, p->n, (long long)slots * G, (int)sizeof(cx<T>), ops->w, box_rows) &&
@@ -1046,7 +1057,8 @@ int mul_fft2(lp2d_plan* p, const void* in, void* state_out, void* other, const v
 
 template <typename T>
 int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, long long batch, double z,
-                    cudaStream_t s, double* moments = nullptr, double dL = 0.0, bool* moments_done = nullptr) {
+                    cudaStream_t s, double* moments = nullptr, double dL = 0.0, bool* moments_done = nullptr,
+                    void* probe_out = nullptr, long long probe_index = 0) {
     const T sc = (T)(1.0 / (double)p->n);
     {
         // rows: spectrum *= H (state stored back), inverse row transform -> ring; columns: inverse -> field
@@ -1062,9 +1074,10 @@ int propagate_state(lp2d_plan* p, void* spectrum, void* field, void* intensity, 
         // stage's transposed store lands the field in its natural orientation
         st[1].out_t = p->spectrum_t;
         st[1].moments = moments; st[1].dL = dL;                 // (zeroed by the caller; inverse stage only; the per-pass path ignores them)
+        st[1].probe_out = static_cast<T*>(probe_out); st[1].probe_index = probe_index;
         const int rc = (p->spectrum_t || p->fused_prop) ? run_p2<T>(p, st, 2, P2_FAC_H, p->spectrum_t, z, 0.0, batch, s, 2) : -1;
         if (rc >= 0) {
-            if (moments_done != nullptr) *moments_done = (rc == 0 && moments != nullptr);
+            if (moments_done != nullptr) *moments_done = (rc == 0);   // the fused kernel delivered moments and probe
             return rc;
         }
         if (p->spectrum_t) return fail(LP2D_EUNSUPPORTED, "transposed spectrum layout: the fused step kernel does not apply to this call");
@@ -1226,10 +1239,11 @@ int lp2d_propagate_sweep(lp2d_plan* p, void* spectrum, void* field, long long ba
     for (int k = 0; k < nsteps; ++k) {
         bool fused_moments = false;
         double* mk_ = moments_out ? moments_out + (size_t)k * batch * 5 : nullptr;
-        const int rc = p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, nullptr, batch, dz, s, mk_, dL, &fused_moments)
-                                            : propagate_state<double>(p, spectrum, field, nullptr, batch, dz, s, mk_, dL, &fused_moments);
+        void* pk_ = probe_out ? static_cast<char*>(probe_out) + (size_t)k * batch * rsz : nullptr;
+        const int rc = p->dtype == LP2D_C64 ? propagate_state<float>(p, spectrum, field, nullptr, batch, dz, s, mk_, dL, &fused_moments, pk_, probe_index)
+                                            : propagate_state<double>(p, spectrum, field, nullptr, batch, dz, s, mk_, dL, &fused_moments, pk_, probe_index);
         if (rc) return rc;
-        if (probe_out != nullptr) {
+        if (probe_out != nullptr && !fused_moments) {
             char* dst = static_cast<char*>(probe_out) + (size_t)k * batch * rsz;
             const unsigned blocks = (unsigned)((batch + 127) / 128);
             if (p->dtype == LP2D_C64)

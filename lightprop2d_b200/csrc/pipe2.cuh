@@ -57,6 +57,8 @@ struct P2Stage {
     int inverse;         // inverse transform (ignored when mid)
     int in_ring, out_ring;
     int mask_kind;
+    T* probe_out;        // final column stage, or nullptr: probe_out[beam] = |out[probe_index]|^2, the on-axis (or any one) sample
+    long long probe_index;   // a z-sweep reads every step (tests/test_analytics.py:43-50); row * N + column of the natural field
     double* moments;     // final column stage, or nullptr: [beam][5] += sum I, sum x I, sum y I, sum x^2 I, sum y^2 I of the
     double dL;           // stage's output (x = (col - N/2) dL, y = (row - N/2) dL; beam2d.py:680-684, 696-702); zeroed by the host
     int out_t;           // final column stage: out / inten are written TRANSPOSED (line c of the tile = row c of the
@@ -396,6 +398,22 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
         // Moment sums of the intensity, fused into the final stage: a z-sweep reads
         // centroid / D4sigma of every step without another pass over the field.  v[] holds the (unscaled) results.
         if constexpr (MOM && AXIS == AX_COL && !OUT_RING && !MID) {
+            // the line's coordinate and the positions of the thread's results in the natural field
+            const int lf = it.tile * W + lo;
+            if (st.probe_out != nullptr) {
+                const int prow = (int)(st.probe_index / N), pcol = (int)(st.probe_index % N);
+                const int want_line = OUT_T ? prow : pcol, want_pos = OUT_T ? pcol : prow;
+                if (lf == want_line) {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) {
+                        const int pos = REV ? ((N - to - TPL * m) & (N - 1)) : to + TPL * m;
+                        if (pos == want_pos) {
+                            const cx<T> val = cscale(v[m], st.scale);
+                            st.probe_out[b] = val.x * val.x + val.y * val.y;
+                        }
+                    }
+                }
+            }
             if (st.moments != nullptr && s_mom != nullptr) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;                        // sums over the thread's positions along the line
 #pragma unroll
@@ -406,7 +424,7 @@ __device__ __forceinline__ void t3_item(const P2Args<T>& p, const P2Item it, cx<
                     const double u = (double)(pos - N / 2) * st.dL;
                     s0 += I; s1 += u * I; s2 += u * u * I;
                 }
-                const double w = (double)(it.tile * W + lo - N / 2) * st.dL;   // coordinate of the line itself
+                const double w = (double)(lf - N / 2) * st.dL;               // coordinate of the line itself
                 // natural store: the line is a grid column (x = w), positions are rows (y); transposed: the other way
                 double a[5] = {s0, OUT_T ? s1 : w * s0, OUT_T ? w * s0 : s1, OUT_T ? s2 : w * w * s0, OUT_T ? w * w * s0 : s2};
 #pragma unroll
@@ -605,8 +623,8 @@ __global__ void __launch_bounds__(T3Cfg<T, N, E, W>::THREADS, MINB) t3_kernel(co
             else t3_item<T, N, E, W, HOOKS, 0, AX_ROW, false, true, false, false>(p, it, xbuf, tid);
         } else if (it.s == 1) {
             if (p.st[1].mid) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, true, true, false>(p, it, xbuf, tid);
-            else if (p.st[1].moments != nullptr && p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true, true>(p, it, xbuf, tid, s_mom);
-            else if (p.st[1].moments != nullptr) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, false, true>(p, it, xbuf, tid, s_mom);
+            else if ((p.st[1].moments != nullptr || p.st[1].probe_out != nullptr) && p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true, true>(p, it, xbuf, tid, s_mom);
+            else if (p.st[1].moments != nullptr || p.st[1].probe_out != nullptr) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, false, true>(p, it, xbuf, tid, s_mom);
             else if (p.st[1].out_t && p.st[1].inverse) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, true, true>(p, it, xbuf, tid, s_mom);
             else if (p.st[1].out_t) t3_item<T, N, E, W, HOOKS, 1, AX_COL, true, false, false, false, true>(p, it, xbuf, tid, s_mom);
             else if (p.use_tma && p.st[1].inverse) t3_col_tma_item<T, N, E, W, true>(p, it, xbuf, &s_bar, tma_parity, tid);

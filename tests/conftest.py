@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The parity tests use small batches; by default such launches are routed to the one-kernel-per-pass path (they do not
+# fill the GPU, include/lp2d.h / DESIGN.md 5d).  The suite keeps them on the fused step kernel so that it stays covered;
+# test_small_launches_take_the_per_pass_path checks the default routing.
+os.environ.setdefault("LP2D_FUSED_MIN", "0")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

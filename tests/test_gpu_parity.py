@@ -1229,3 +1229,37 @@ def test_h_plane_in_the_fresh_chain_and_across_streams(bits, n, monkeypatch):
     for k, (x, y) in enumerate(zip(out["0"], out["1"])):
         err = float((x - y).abs().max() / x.abs().max())
         assert err <= (2e-6 if bits == 64 else 1e-14), (k, err)
+
+
+@pytest.mark.parametrize("bits,n", [(64, 1024), (64, 512), (128, 256)])
+def test_small_launches_take_the_per_pass_path(bits, n, monkeypatch):
+    """Default routing (LP2D_FUSED_MIN=75): a single field does not fill the GPU and runs as two plain launches per step
+    instead of the fused step kernel; a large batch runs fused (one launch).  Same values up to rounding either way."""
+    from lightprop2d_b200 import beam2d as _b
+    lib = _lib.load()
+    ct = torch.complex64 if bits == 64 else torch.complex128
+    torch.manual_seed(9)
+    big = 64 if n == 1024 else 512
+    f = torch.randn(big, n, n, dtype=ct, device="cuda")
+    res = {}
+    for mode in ("75", "0"):
+        monkeypatch.setenv("LP2D_FUSED_MIN", mode)
+        monkeypatch.setenv("LP2D_HPLANE", "0")
+        _b._PLAN_CACHE.clear()
+        b = Beam2D(0.4 * n / 1024, n, 532e-7, init_field=f[:1], complex_bits=bits, use_gpu=True)
+        plan = b._plan.handle
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        s = f.clone(); o = torch.empty_like(f)
+        _lib.check(lib.lp2d_propagate(plan, s.data_ptr(), o.data_ptr(), None, 1, 0.02, st), "warm-up")
+        _lib.check(lib.lp2d_propagate(plan, s.data_ptr(), o.data_ptr(), None, big, 0.02, st), "warm-up (factor plane of the fused kernel)")
+        s.copy_(f)
+        l0 = lib.lp2d_launch_count()
+        _lib.check(lib.lp2d_propagate(plan, s.data_ptr(), o.data_ptr(), None, 1, 0.02, st), "single field")
+        l1 = lib.lp2d_launch_count()
+        _lib.check(lib.lp2d_propagate(plan, s.data_ptr(), o.data_ptr(), None, big, 0.02, st), "batch")
+        l2 = lib.lp2d_launch_count()
+        res[mode] = (o.cpu().numpy(), l1 - l0, l2 - l1)
+    _b._PLAN_CACHE.clear()
+    assert res["0"][1] == 1 and res["0"][2] == 1                  # always fused: one launch
+    assert res["75"][1] == 2 and res["75"][2] == 1                # default: the single field as row pass + column pass
+    assert rel_l2(res["75"][0], res["0"][0]) <= (2e-6 if bits == 64 else 1e-14)
