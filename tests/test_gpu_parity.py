@@ -1263,3 +1263,34 @@ def test_small_launches_take_the_per_pass_path(bits, n, monkeypatch):
     assert res["0"][1] == 1 and res["0"][2] == 1                  # always fused: one launch
     assert res["75"][1] == 2 and res["75"][2] == 1                # default: the single field as row pass + column pass
     assert rel_l2(res["75"][0], res["0"][0]) <= (2e-6 if bits == 64 else 1e-14)
+
+
+@pytest.mark.parametrize("bits", BITS)
+@pytest.mark.parametrize("n", [256, 512, 1024])
+def test_single_field_default_routing_vs_oracle(bits, n, monkeypatch):
+    """The library's DEFAULT routing for a single field (two plain launches + the H plane from the second equal step on;
+    the suite otherwise pins LP2D_FUSED_MIN=0): README-style chain, lens, filters and a z-sweep against the oracle."""
+    from lightprop2d_b200 import beam2d as _b
+    monkeypatch.delenv("LP2D_FUSED_MIN", raising=False)
+    _b._PLAN_CACHE.clear()
+    try:
+        np.random.seed(3)
+        b = Beam2D(200 * um * n / 256, n, 632 * nm, init_field_gen=lp.random_round_hole, init_gen_args=(25 * um * n / 256,), complex_bits=bits)
+        np.random.seed(3)
+        o = orc.OracleBeam(200 * um * n / 256, n, 632 * nm, init_field_gen=lp.random_round_hole, init_gen_args=(25 * um * n / 256,),
+                           complex_bits=bits)
+        b.propagate(100 * um); o.propagate(100 * um)
+        assert rel_l2(b.field, o.field) <= TOL[bits] and rel_l2(b.spectrum, o.spectrum) <= TOL[bits]
+        b.lens(0.05); o.lens(0.05)
+        for _ in range(4):                                    # equal steps: the H plane serves the later ones
+            b.propagate(30 * um); o.propagate(30 * um)
+        assert rel_l2(b.field, o.field) <= TOL[bits] and rel_l2(b.iprofile, o.iprofile) <= TOL[bits]
+        b.coordinate_filter(f_gen=lp.round_hole, fargs=(60 * um * n / 256,)); o.coordinate_filter(f_gen=lp.round_hole, fargs=(60 * um * n / 256,))
+        I, M = b.propagate_sweep(20 * um, 3, probe="centre", moments=True)
+        for _ in range(3):
+            o.propagate(20 * um)
+        assert rel_l2(b.field, o.field) <= TOL[bits]
+        assert np.allclose(I[-1], o.iprofile[n // 2, n // 2], rtol=1e-4 if bits == 64 else 1e-10)
+        assert np.allclose(M["centroid"][-1], o.centroid[:2], rtol=1e-4, atol=1e-9)
+    finally:
+        _b._PLAN_CACHE.clear()
